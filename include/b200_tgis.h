@@ -1,0 +1,104 @@
+/* b200_tgis.h — C ABI of the B200-native TGIS decode hot path (libb200_tgis.so).
+ *
+ * Conventions (SURVEY.md §8b "Op / C-ABI"):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host"
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*): no host synchronisation, no
+ *     allocation — outputs and workspaces are caller-provided; all entry points are CUDA-graph capturable
+ *   - returns 0 (B200_OK) or a negative error code; b200_last_error() gives the message (thread-local)
+ *   - fp16 tensors are row-major `__half`; token-major activations [T, features]
+ * Each entry point names the reference interface it replaces (paths under
+ * /root/reference/server/text_generation_server/).
+ */
+#ifndef B200_TGIS_H_
+#define B200_TGIS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_UNSUPPORTED (-3)
+#define B200_ERR_NOMEM (-4)
+
+#define B200_KV_PAGE_TOKENS 16 /* models/paged_causal_lm.py:308 */
+
+int b200_abi_version(void);
+const char* b200_last_error(void);
+
+/* ---- fused residual-add + RMSNorm ---------------------------------------------------------------------
+ * replaces dropout_layer_norm.dropout_add_ln_fwd(h, residual, gamma, None x5, 0.0, eps, 1.0, 0, None, False, True)
+ * (models/custom_modeling/flash_llama_modeling.py:132-148).  residual may be NULL (first layer, :149-150; then
+ * residual_out is not written and the caller aliases it to h). */
+int b200_rmsnorm_residual(const void* h, const void* residual, const void* gamma, void* normed_out, void* residual_out,
+                          int64_t T, int64_t H, float eps, void* stream);
+
+/* ---- RoPE + paged KV write ----------------------------------------------------------------------------
+ * replaces rotary_emb.apply_rotary(x1, x2, cos, sin, x1, x2, False) on q and k (utils/layers.py:466-472,
+ * flash_llama_modeling.py:262-263) and the KV append (flash_llama_modeling.py:268,282; fms-extras
+ * reshape_and_cache via paged_llama_modeling.py:250).
+ * qkv [T, (n_heads + 2 n_kv) * d] is rotated in place (q and k parts); k and v are scattered into the pools at
+ * slot_mapping[t] = block * 16 + offset (negative = skip).  cos/sin: fp16 tables [max_pos, d/2] indexed by
+ * position_ids (utils/layers.py:453-464).  Pool layout: [num_blocks][n_kv][16][d] fp16, 16-byte chunks XOR-swizzled
+ * by (token & 7) (DESIGN.md "KV page layout"). */
+int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
+                             const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads, int n_kv_heads,
+                             int head_dim, void* stream);
+
+/* ---- SiLU(gate) * up   (flash_llama_modeling.py:332-335); gate_up [T, 2, I] -> out [T, I] */
+int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t I, void* stream);
+
+/* ---- vocabulary-parallel embedding gather (TensorParallelEmbedding.forward, utils/layers.py:346-357):
+ * out[t] = table[ids[t] - vocab_start] if in [0, vocab_rows) else 0 */
+int b200_embedding(const void* table, const int64_t* ids, void* out, int64_t T, int64_t H, int64_t vocab_start,
+                   int64_t vocab_rows, void* stream);
+
+/* ---- greedy arg-max over fp16 logits rows (Greedy, utils/tokens.py:44-46); ld = row stride in halves */
+int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, void* stream);
+
+/* ---- decode attention over the paged KV pool ----------------------------------------------------------
+ * replaces attention(q, layer_past[:,0], layer_past[:,1], cu_seqlens, max_s, scale, cu_seqlens_q, 1, False)
+ * (utils/flash_attn.py:43-127 <- flash_llama_modeling.py:285-295) and fms-extras paged_attention
+ * (paged_llama_modeling.py:267).  q: one token per sequence, head-major [n_heads][d] at q + b*q_token_stride (halves).
+ * block_table[b][i] = pool block of the i-th 16-token page; context_lens[b] includes the token just written.
+ * out[b] at out + b*out_token_stride.  workspace >= b200_attn_decode_workspace_bytes(...). */
+int64_t b200_attn_decode_workspace_bytes(int B, int n_heads, int head_dim, int max_context_len);
+int b200_attn_decode_paged(const void* q, int64_t q_token_stride, const void* k_pool, const void* v_pool,
+                           const int32_t* block_table, int64_t block_table_stride, const int32_t* context_lens, void* out,
+                           int64_t out_token_stride, void* workspace, int64_t workspace_bytes, int B, int n_heads,
+                           int n_kv_heads, int head_dim, int max_context_len, float softmax_scale, void* stream);
+
+/* ---- varlen prefill attention -------------------------------------------------------------------------
+ * replaces attention(q, k, v, cu_seqlens, max_s, softmax_scale) (utils/flash_attn.py:43-127 <-
+ * flash_llama_modeling.py:271-278; flash_attn_2_cuda.varlen_fwd).  Strides in halves between tokens. */
+int b200_attn_prefill_varlen(const void* q, int64_t q_token_stride, const void* k, int64_t k_token_stride, const void* v,
+                             int64_t v_token_stride, const int32_t* cu_seqlens, void* out, int64_t out_token_stride, int B,
+                             int max_s, int n_heads, int n_kv_heads, int head_dim, float softmax_scale, int causal, void* stream);
+
+/* ---- linears ------------------------------------------------------------------------------------------
+ * workspace: >= b200_gemm_workspace_bytes(T, N, K) bytes; its first 64 KiB must have been zeroed once (split-K tile
+ * counters; the kernels re-arm them).  NULL disables split-K. */
+int64_t b200_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K);
+
+/* y[T,N] = x[T,K] . w[N,K]^T (+ bias[N]);  replaces F.linear in FastLinear.forward (utils/layers.py:110-111) and
+ * torch.mm in TensorParallelHead.forward (:257-262). */
+int b200_gemm_f16(const void* x, const void* w, const void* bias, void* y, int64_t T, int64_t N, int64_t K, void* workspace,
+                  void* stream);
+
+/* one-time in-place nibble re-order of GPTQ qweight int32 [K/8, N]; replaces exllamav2_kernels.make_q_matrix
+ * (utils/gptq/exllamav2.py:23-62).  inverse != 0 restores the checkpoint layout. */
+int b200_gptq_repack(void* qweight, int64_t K, int64_t N, int inverse, void* stream);
+
+/* y[T,N] = x[T,K] . dequant(qweight, qzeros, scales) (+ bias);  replaces exllamav2_kernels.gemm_half_q_half
+ * (utils/gptq/exllamav2.py:14-20).  qzeros int32 [K/g, N/8], scales fp16 [K/g, N] in checkpoint layout;
+ * groups are k // groupsize (trivial g_idx; act-order is rejected by the host wrapper). */
+int b200_gemm_w4a16(const void* x, const void* qweight_repacked, const void* qzeros, const void* scales, const void* bias,
+                    void* y, int64_t T, int64_t N, int64_t K, int groupsize, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_TGIS_H_ */

@@ -1,0 +1,5 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this package.
+The product path (text-generation-inference_b200/) never does; it fails loudly without the CUDA library.
+"""

@@ -1,0 +1,279 @@
+// HBM-bound row kernels of the decode step: fused residual-add + RMSNorm, RoPE + paged KV write,
+// SiLU*mul, vocabulary-parallel embedding gather, greedy arg-max.
+//
+// Reference ops replaced (paths under /root/reference/server/text_generation_server/):
+//   rmsnorm_residual ......... dropout_layer_norm.dropout_add_ln_fwd, models/custom_modeling/flash_llama_modeling.py:132-148
+//   rope_kv_write_paged ...... rotary_emb.apply_rotary (utils/layers.py:466-472) + KV append
+//                              (flash_llama_modeling.py:268,282) / fms-extras reshape_and_cache (paged_llama_modeling.py:250)
+//   silu_mul ................. flash_llama_modeling.py:332-335
+//   embedding ................ TensorParallelEmbedding.forward, utils/layers.py:346-357
+//   argmax ................... Greedy, utils/tokens.py:44-46
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// residual-add + RMSNorm.  One CTA per token row; 8 halves (16 B) per thread per iteration.
+// fp32 statistics on the un-rounded sum.
+// Optional split-K input: `h` may be `n_parts` fp32 partial matrices [n_parts][T][H] (gemm split-K
+// workspace); they are summed and rounded to fp16 first, which is exactly the GEMM's fp16 output.
+// ------------------------------------------------------------------------------------------------
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) rmsnorm_residual_kernel(const __half* __restrict__ h,
+                                                                      const __half* __restrict__ residual,
+                                                                      const __half* __restrict__ gamma,
+                                                                      __half* __restrict__ normed, __half* __restrict__ res_out,
+                                                                      int H, float eps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of the summed row
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const __half* hp = h + (size_t)row * H;
+  const __half* rp = residual ? residual + (size_t)row * H : nullptr;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < H; i += kThreads * 8) {
+    uint4 hv = *reinterpret_cast<const uint4*>(hp + i);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(h2[j]);
+      x[2 * j] = f.x;
+      x[2 * j + 1] = f.y;
+    }
+    if (rp) {
+      uint4 rv = *reinterpret_cast<const uint4*>(rp + i);
+      const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(r2[j]);
+        x[2 * j] += f.x;
+        x[2 * j + 1] += f.y;
+      }
+      uint4 ov;
+      __half2* o2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      *reinterpret_cast<uint4*>(res_out + (size_t)row * H + i) = ov;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xs[i + j] = x[j];
+      ss += x[j] * x[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane_id() == 0) red[warp_id()] = ss;
+  __syncthreads();
+  if (warp_id() == 0) {
+    float v = lane_id() < kThreads / 32 ? red[lane_id()] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float rstd = rsqrtf(red[0] / (float)H + eps);
+  for (int i = threadIdx.x * 8; i < H; i += kThreads * 8) {
+    uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
+    const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+    uint4 ov;
+    __half2* o2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 g = __half22float2(g2[j]);
+      o2[j] = __floats2half2_rn(xs[i + 2 * j] * rstd * g.x, xs[i + 2 * j + 1] * rstd * g.y);
+    }
+    *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = ov;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (half-split pairs, fp32 math, fp16 tables gathered by position) applied in place to q and k of
+// the fused qkv activation, plus the scatter of k and v into the paged pool.
+// Pool layout per layer: K,V [num_blocks][n_kv][16 tokens][d] fp16, 16-byte chunks XOR-swizzled with
+// (token & 7) so a page-head tile lands bank-conflict-free in shared memory with one bulk copy.
+// grid = (T, n_heads + 2*n_kv); block = d/2 threads... one thread per rotation pair.
+// ------------------------------------------------------------------------------------------------
+template <int kHeadDim>
+__global__ void rope_kv_write_kernel(__half* __restrict__ qkv, const __half* __restrict__ cos_t,
+                                     const __half* __restrict__ sin_t, const int64_t* __restrict__ position_ids,
+                                     const int64_t* __restrict__ slot_mapping, __half* __restrict__ k_pool,
+                                     __half* __restrict__ v_pool, int n_heads, int n_kv, int rot_half) {
+  const int t = blockIdx.x;
+  const int head = blockIdx.y;  // [0,h): q, [h,h+kv): k, [h+kv, h+2kv): v
+  const int j = threadIdx.x;    // pair index 0..d/2-1
+  __half* base = qkv + ((size_t)t * (n_heads + 2 * n_kv) + head) * kHeadDim;
+  const bool is_v = head >= n_heads + n_kv;
+  __half lo = base[j], hi = base[j + kHeadDim / 2];
+  if (!is_v) {
+    // rotary_dim = cos.shape[-1] = rot_half: x1 = x[:rot_half], x2 = x[rot_half:2*rot_half]
+    // kernel is instantiated for full rotation (rot_half == d/2), the Llama case.
+    const int64_t pos = position_ids[t];
+    const float c = __half2float(cos_t[pos * rot_half + j]);
+    const float s = __half2float(sin_t[pos * rot_half + j]);
+    const float x1 = __half2float(lo), x2 = __half2float(hi);
+    lo = __float2half_rn(x1 * c - x2 * s);
+    hi = __float2half_rn(x1 * s + x2 * c);
+    base[j] = lo;
+    base[j + kHeadDim / 2] = hi;
+  }
+  if (head >= n_heads) {
+    const int64_t slot = slot_mapping[t];
+    if (slot < 0) return;  // padding token
+    const int64_t blk = slot / kPageTokens;
+    const int tok = (int)(slot % kPageTokens);
+    const int hk = is_v ? head - n_heads - n_kv : head - n_heads;
+    __half* pool = is_v ? v_pool : k_pool;
+    unsigned char* tile = reinterpret_cast<unsigned char*>(pool + ((size_t)blk * n_kv + hk) * kPageTokens * kHeadDim);
+    const int e_lo = j, e_hi = j + kHeadDim / 2;
+    *reinterpret_cast<__half*>(tile + kv_swizzled_chunk_offset<kHeadDim>(tok, e_lo >> 3) + (e_lo & 7) * 2) = lo;
+    *reinterpret_cast<__half*>(tile + kv_swizzled_chunk_offset<kHeadDim>(tok, e_hi >> 3) + (e_hi & 7) * 2) = hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[t, i] = fp16( fp16(silu(g)) * u ),  gate_up [T, 2, I]
+// ------------------------------------------------------------------------------------------------
+__global__ void silu_mul_kernel(const __half* __restrict__ gate_up, __half* __restrict__ out, int64_t I, int64_t total8) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total8; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t per_row = I / 8;
+    const int64_t t = idx / per_row;
+    const int64_t i = (idx % per_row) * 8;
+    uint4 gv = *reinterpret_cast<const uint4*>(gate_up + t * 2 * I + i);
+    uint4 uv = *reinterpret_cast<const uint4*>(gate_up + t * 2 * I + I + i);
+    const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+    const __half2* u2 = reinterpret_cast<const __half2*>(&uv);
+    uint4 ov;
+    __half2* o2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 g = __half22float2(g2[j]);
+      // torch fp16 SiLU: fp32 x / (1 + exp(-x)), one rounding; then an fp16 multiply
+      __half2 a = __floats2half2_rn(g.x / (1.f + expf(-g.x)), g.y / (1.f + expf(-g.y)));
+      o2[j] = __hmul2(a, u2[j]);
+    }
+    *reinterpret_cast<uint4*>(out + t * I + i) = ov;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[t] = (vocab_start <= id < vocab_start + rows) ? table[id - vocab_start] : 0
+// ------------------------------------------------------------------------------------------------
+__global__ void embedding_kernel(const __half* __restrict__ table, const int64_t* __restrict__ ids, __half* __restrict__ out,
+                                 int H, int64_t vocab_start, int64_t rows) {
+  const int t = blockIdx.x;
+  const int64_t id = ids[t] - vocab_start;
+  const bool ok = id >= 0 && id < rows;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    uint4 v = ok ? *reinterpret_cast<const uint4*>(table + id * H + i) : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(out + (size_t)t * H + i) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy arg-max over fp16 logits (first index wins ties, like torch.argmax on a row scan)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) argmax_kernel(const __half* __restrict__ logits, int64_t* __restrict__ out, int64_t V,
+                                                       int64_t ld) {
+  const __half* row = logits + (size_t)blockIdx.x * ld;
+  float best = -INFINITY;
+  int64_t best_i = 0x7fffffffffffffffLL;
+  const int64_t V8 = V & ~7LL;
+  for (int64_t i = (int64_t)threadIdx.x * 8; i < V8; i += 256 * 8) {
+    uint4 v = *reinterpret_cast<const uint4*>(row + i);
+    const __half* hv = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = __half2float(hv[j]);
+      if (f > best || (f == best && i + j < best_i)) { best = f; best_i = i + j; }
+    }
+  }
+  for (int64_t i = V8 + threadIdx.x; i < V; i += 256) {
+    float f = __half2float(row[i]);
+    if (f > best || (f == best && i < best_i)) { best = f; best_i = i; }
+  }
+  __shared__ float sv[8];
+  __shared__ int64_t si[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int64_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if (lane_id() == 0) { sv[warp_id()] = best; si[warp_id()] = best_i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < best_i)) { best = sv[w]; best_i = si[w]; }
+    out[blockIdx.x] = best_i == 0x7fffffffffffffffLL ? 0 : best_i;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_rmsnorm_residual(const void* h, const void* residual, const void* gamma, void* normed_out,
+                                     void* residual_out, int64_t T, int64_t H, float eps, void* stream) {
+  if (T == 0) return B200_OK;
+  if (H % 8 != 0 || H > 16384 || !h || !gamma || !normed_out || (residual && !residual_out)) {
+    b200_set_last_error("rmsnorm_residual: need H % 8 == 0, H <= 16384, non-null h/gamma/out");
+    return B200_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)H * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(rmsnorm_residual_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  rmsnorm_residual_kernel<256><<<(unsigned)T, 256, smem, st>>>((const __half*)h, (const __half*)residual, (const __half*)gamma,
+                                                               (__half*)normed_out, (__half*)residual_out, (int)H, eps);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
+                                        const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads,
+                                        int n_kv_heads, int head_dim, void* stream) {
+  if (T == 0) return B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)T, n_heads + 2 * n_kv_heads);
+  if (head_dim == 128) {
+    rope_kv_write_kernel<128><<<grid, 64, 0, st>>>((__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids, slot_mapping,
+                                                   (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 64);
+  } else if (head_dim == 64) {
+    rope_kv_write_kernel<64><<<grid, 32, 0, st>>>((__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids, slot_mapping,
+                                                  (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 32);
+  } else {
+    b200_set_last_error("rope_kv_write_paged: head_dim must be 64 or 128");
+    return B200_ERR_UNSUPPORTED;
+  }
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t I, void* stream) {
+  if (T == 0) return B200_OK;
+  if (I % 8 != 0) { b200_set_last_error("silu_mul: I % 8 != 0"); return B200_ERR_ARG; }
+  const int64_t total8 = T * I / 8;
+  int64_t blocks = (total8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  silu_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_up, (__half*)out, I, total8);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_embedding(const void* table, const int64_t* ids, void* out, int64_t T, int64_t H, int64_t vocab_start,
+                              int64_t vocab_rows, void* stream) {
+  if (T == 0) return B200_OK;
+  if (H % 8 != 0) { b200_set_last_error("embedding: H % 8 != 0"); return B200_ERR_ARG; }
+  embedding_kernel<<<(unsigned)T, 128, 0, (cudaStream_t)stream>>>((const __half*)table, ids, (__half*)out, (int)H, vocab_start, vocab_rows);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, void* stream) {
+  if (B == 0) return B200_OK;
+  if (ld % 8 != 0) { b200_set_last_error("argmax: row stride must be a multiple of 8 halves"); return B200_ERR_ARG; }
+  argmax_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, out_ids, V, ld);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}

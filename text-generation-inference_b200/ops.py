@@ -1,0 +1,199 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch only supplies device memory and the current stream.
+
+Every function requires CUDA tensors and raises if the library is missing — no eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+PAGE = 16
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.B200Error(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.B200Error(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def rmsnorm_residual(h: torch.Tensor, residual: Optional[torch.Tensor], gamma: torch.Tensor, eps: float
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(normed, residual_out) — LlamaRMSNorm.forward semantics (flash_llama_modeling.py:113-152)."""
+    _req(h, torch.float16, "h")
+    h = h.contiguous()
+    T, H = h.shape
+    normed = torch.empty_like(h)
+    if residual is not None:
+        residual = residual.contiguous()
+        res_out = torch.empty_like(h)
+    else:
+        res_out = None
+    _lib.check(_lib.load().b200_rmsnorm_residual(_ptr(h), _ptr(residual), _ptr(gamma), _ptr(normed), _ptr(res_out),
+                                                 T, H, float(eps), _stream()), "rmsnorm_residual")
+    return normed, (res_out if res_out is not None else h)
+
+
+def rope_kv_write_paged(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position_ids: torch.Tensor,
+                        slot_mapping: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, n_heads: int,
+                        n_kv_heads: int, head_dim: int) -> None:
+    _req(qkv, torch.float16, "qkv")
+    _req(position_ids, torch.int64, "position_ids")
+    _req(slot_mapping, torch.int64, "slot_mapping")
+    assert qkv.is_contiguous() and cos.is_contiguous() and sin.is_contiguous()
+    T = qkv.shape[0]
+    _lib.check(_lib.load().b200_rope_kv_write_paged(_ptr(qkv), _ptr(cos), _ptr(sin), _ptr(position_ids), _ptr(slot_mapping),
+                                                    _ptr(k_pool), _ptr(v_pool), T, n_heads, n_kv_heads, head_dim, _stream()),
+               "rope_kv_write_paged")
+
+
+def silu_mul(gate_up: torch.Tensor) -> torch.Tensor:
+    _req(gate_up, torch.float16, "gate_up")
+    T, I2 = gate_up.shape
+    out = torch.empty(T, I2 // 2, dtype=torch.float16, device=gate_up.device)
+    _lib.check(_lib.load().b200_silu_mul(_ptr(gate_up.contiguous()), _ptr(out), T, I2 // 2, _stream()), "silu_mul")
+    return out
+
+
+def embedding(table: torch.Tensor, ids: torch.Tensor, vocab_start: int = 0) -> torch.Tensor:
+    _req(table, torch.float16, "table")
+    _req(ids, torch.int64, "ids")
+    out = torch.empty(ids.shape[0], table.shape[1], dtype=torch.float16, device=table.device)
+    _lib.check(_lib.load().b200_embedding(_ptr(table), _ptr(ids), _ptr(out), ids.shape[0], table.shape[1], vocab_start,
+                                          table.shape[0], _stream()), "embedding")
+    return out
+
+
+def argmax(logits: torch.Tensor) -> torch.Tensor:
+    _req(logits, torch.float16, "logits")
+    B, V = logits.shape
+    assert logits.stride(1) == 1
+    out = torch.empty(B, dtype=torch.int64, device=logits.device)
+    _lib.check(_lib.load().b200_argmax(_ptr(logits), _ptr(out), B, V, logits.stride(0), _stream()), "argmax")
+    return out
+
+
+def attn_decode_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_table: torch.Tensor,
+                      context_lens: torch.Tensor, max_context_len: int, softmax_scale: float, n_kv_heads: int,
+                      out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B, n_heads, d] (may be a strided view of the fused qkv activation: stride(0) arbitrary, inner contiguous)."""
+    _req(q, torch.float16, "q")
+    _req(block_table, torch.int32, "block_table")
+    _req(context_lens, torch.int32, "context_lens")
+    B, h, d = q.shape
+    assert q.stride(2) == 1 and q.stride(1) == d
+    if out is None:
+        out = torch.empty(B, h, d, dtype=torch.float16, device=q.device)
+    lib = _lib.load()
+    need = lib.b200_attn_decode_workspace_bytes(B, h, d, max_context_len)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
+    _lib.check(lib.b200_attn_decode_paged(_ptr(q), q.stride(0), _ptr(k_pool), _ptr(v_pool), _ptr(block_table),
+                                          block_table.stride(0), _ptr(context_lens), _ptr(out), out.stride(0), _ptr(workspace),
+                                          workspace.numel() * workspace.element_size(), B, h, n_kv_heads, d, max_context_len,
+                                          float(softmax_scale), _stream()), "attn_decode_paged")
+    return out
+
+
+def attn_prefill_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens: torch.Tensor, max_s: int,
+                        softmax_scale: float, causal: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [T,h,d], k/v [T,h_kv,d]: strided views allowed (inner two dims contiguous)."""
+    _req(q, torch.float16, "q")
+    _req(cu_seqlens, torch.int32, "cu_seqlens")
+    T, h, d = q.shape
+    h_kv = k.shape[1]
+    for t in (q, k, v):
+        assert t.stride(2) == 1 and t.stride(1) == d
+    if out is None:
+        out = torch.empty(T, h, d, dtype=torch.float16, device=q.device)
+    _lib.check(_lib.load().b200_attn_prefill_varlen(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
+                                                    _ptr(cu_seqlens), _ptr(out), out.stride(0), cu_seqlens.shape[0] - 1, max_s,
+                                                    h, h_kv, d, float(softmax_scale), int(causal), _stream()),
+               "attn_prefill_varlen")
+    return out
+
+
+_gemm_ws = {}
+
+
+def gemm_workspace(device, T: int, N: int, K: int) -> torch.Tensor:
+    """Per-device split-K workspace (counters zeroed once; the kernels re-arm them)."""
+    need = _lib.load().b200_gemm_workspace_bytes(T, N, K)
+    ws = _gemm_ws.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _gemm_ws[device] = ws
+    return ws
+
+
+def gemm_f16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T,K] @ w[N,K]^T -> [T,N] fp16."""
+    _req(x, torch.float16, "x")
+    _req(w, torch.float16, "w")
+    assert x.is_contiguous() and w.is_contiguous()
+    T, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(T, N, dtype=torch.float16, device=x.device)
+    if workspace is None:
+        workspace = gemm_workspace(x.device, T, N, K)
+    _lib.check(_lib.load().b200_gemm_f16(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), T, N, K, _ptr(workspace), _stream()), "gemm_f16")
+    return out
+
+
+def gptq_repack(qweight: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    _req(qweight, torch.int32, "qweight")
+    assert qweight.is_contiguous()
+    Kw, N = qweight.shape
+    _lib.check(_lib.load().b200_gptq_repack(_ptr(qweight), Kw * 8, N, int(inverse), _stream()), "gptq_repack")
+    return qweight
+
+
+def gemm_w4a16(x: torch.Tensor, qweight_repacked: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, groupsize: int,
+               bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, torch.float16, "x")
+    _req(qweight_repacked, torch.int32, "qweight")
+    _req(qzeros, torch.int32, "qzeros")
+    _req(scales, torch.float16, "scales")
+    assert x.is_contiguous() and qweight_repacked.is_contiguous() and qzeros.is_contiguous() and scales.is_contiguous()
+    T, K = x.shape
+    N = qweight_repacked.shape[1]
+    if out is None:
+        out = torch.empty(T, N, dtype=torch.float16, device=x.device)
+    if workspace is None:
+        workspace = gemm_workspace(x.device, T, N, K)
+    _lib.check(_lib.load().b200_gemm_w4a16(_ptr(x), _ptr(qweight_repacked), _ptr(qzeros), _ptr(scales), _ptr(bias), _ptr(out),
+                                           T, N, K, groupsize, _ptr(workspace), _stream()), "gemm_w4a16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# KV pool helpers (layout documented in DESIGN.md; used by tests and the block manager)
+# ------------------------------------------------------------------------------------------------------
+def kv_pool_alloc(num_blocks: int, n_kv_heads: int, head_dim: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    shape = (num_blocks, n_kv_heads, PAGE, head_dim)
+    return (torch.zeros(shape, dtype=torch.float16, device=device), torch.zeros(shape, dtype=torch.float16, device=device))
+
+
+def kv_pool_unswizzle(pool: torch.Tensor) -> torch.Tensor:
+    """Logical [num_blocks, n_kv, 16, d] view of a swizzled pool (test/debug helper; not on the hot path)."""
+    nb, hk, pg, d = pool.shape
+    chunks = pool.view(nb, hk, pg, d // 8, 8)
+    t = torch.arange(pg, device=pool.device)
+    c = torch.arange(d // 8, device=pool.device)
+    phys = (c[None, :] ^ (t[:, None] & 7))  # [16, d/8] physical chunk of logical chunk c at token t
+    idx = phys[None, None, :, :, None].expand(nb, hk, pg, d // 8, 8)
+    return torch.gather(chunks, 3, idx).reshape(nb, hk, pg, d)
