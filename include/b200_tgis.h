@@ -28,6 +28,18 @@ extern "C" {
 
 int b200_abi_version(void);
 const char* b200_last_error(void);
+/* number of kernels this library has enqueued in this process (bench.py reports the delta as "gpu_launches") */
+int64_t b200_launch_count(void);
+
+/* ---- per-kernel device timing (bench.py roofline): CUDA events on the launching stream around every launch of one
+ * kernel family while a handle is attached.  collect() synchronises and returns the launch count. */
+#define B200_TIME_ATTN_DECODE 1
+#define B200_TIME_GEMM_W4A16 2
+#define B200_TIME_GEMM_F16 3
+void* b200_timing_create(int max_launches);
+void b200_timing_destroy(void* timing);
+void b200_timing_attach(void* timing /* NULL detaches */, int which);
+int b200_timing_collect(void* timing, float* total_ms /* host */);
 
 /* ---- fused residual-add + RMSNorm ---------------------------------------------------------------------
  * replaces dropout_layer_norm.dropout_add_ln_fwd(h, residual, gamma, None x5, 0.0, eps, 1.0, 0, None, False, True)
@@ -56,8 +68,10 @@ int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t I, void* st
 int b200_embedding(const void* table, const int64_t* ids, void* out, int64_t T, int64_t H, int64_t vocab_start,
                    int64_t vocab_rows, void* stream);
 
-/* ---- greedy arg-max over fp16 logits rows (Greedy, utils/tokens.py:44-46); ld = row stride in halves */
-int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, void* stream);
+/* ---- greedy arg-max over fp16 logits rows (Greedy, utils/tokens.py:44-46); ld = row stride in halves.
+ * banned_ids (optional, [B]): token whose score counts as -inf for that row, or -1 — the min_new_tokens EOS mask
+ * `scores[idx, eos] = -inf` (utils/tokens.py:244-246) folded into the arg-max. */
+int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, const int64_t* banned_ids, void* stream);
 
 /* ---- decode attention over the paged KV pool ----------------------------------------------------------
  * replaces attention(q, layer_past[:,0], layer_past[:,1], cu_seqlens, max_s, scale, cu_seqlens_q, 1, False)
@@ -82,6 +96,7 @@ int b200_attn_prefill_varlen(const void* q, int64_t q_token_stride, const void* 
  * workspace: >= b200_gemm_workspace_bytes(T, N, K) bytes; its first 64 KiB must have been zeroed once (split-K tile
  * counters; the kernels re-arm them).  NULL disables split-K. */
 int64_t b200_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K);
+int64_t b200_gemm_workspace_bytes_max(int64_t N, int64_t K); /* max over all T: size a persistent workspace with this */
 
 /* y[T,N] = x[T,K] . w[N,K]^T (+ bias[N]);  replaces F.linear in FastLinear.forward (utils/layers.py:110-111) and
  * torch.mm in TensorParallelHead.forward (:257-262). */
@@ -97,6 +112,99 @@ int b200_gptq_repack(void* qweight, int64_t K, int64_t N, int inverse, void* str
  * groups are k // groupsize (trivial g_idx; act-order is rejected by the host wrapper). */
 int b200_gemm_w4a16(const void* x, const void* qweight_repacked, const void* qzeros, const void* scales, const void* bias,
                     void* y, int64_t T, int64_t N, int64_t K, int groupsize, void* workspace, void* stream);
+
+/* ---- paged KV block allocator (host) + per-step bookkeeping (device) -------------------------------------
+ * replaces fms-extras PagedKVCacheManager block bookkeeping (models/paged_causal_lm.py:338-353,
+ * utils/paged.py:92-134; block size 16).  Block ids index the pools' first dimension. */
+void* b200_kv_alloc_create(int32_t num_blocks);
+void b200_kv_alloc_destroy(void* allocator);
+int32_t b200_kv_alloc_num_free(void* allocator);
+int b200_kv_alloc_take(void* allocator, int32_t n, int32_t* out_ids /* host */);
+int b200_kv_alloc_release(void* allocator, const int32_t* ids /* host */, int32_t n);
+/* start of a decode step, per sequence b: pos = context_lens[b]; position_ids[b] = pos;
+ * slot_mapping[b] = block_table[b][pos/16]*16 + pos%16; context_lens[b] = pos+1; input_ids[b] = next_ids[b]
+ * (next_ids/input_ids may be NULL).  context_lens[b] < 0 marks a padding row (slot -1). */
+int b200_decode_advance(const int32_t* block_table, int64_t block_table_stride, int32_t* context_lens, int64_t* position_ids,
+                        int64_t* slot_mapping, const int64_t* next_ids, int64_t* input_ids, int B, void* stream);
+
+/* ---- FlashLlama step runtime ---------------------------------------------------------------------------
+ * One call enqueues a whole prefill / decode step of the Llama graph; replaces the Python op sequence of
+ * FlashLlamaForCausalLM.forward (models/custom_modeling/flash_llama_modeling.py:425-540).  All pointers device
+ * memory owned by the caller (weights: the model; scratch: the host runtime). */
+typedef struct {
+  const void* weight;  /* fp16 [N, K], or NULL when GPTQ */
+  const void* qweight; /* int32 [K/8, N] after b200_gptq_repack, or NULL */
+  const void* qzeros;  /* int32 [K/g, N/8] */
+  const void* scales;  /* fp16 [K/g, N] */
+  const void* bias;    /* fp16 [N] or NULL */
+  int64_t N, K;
+  int32_t groupsize;
+  int32_t _pad;
+} B200Linear;
+
+typedef struct {
+  const void* input_ln; /* fp16 [H] */
+  const void* post_ln;
+  B200Linear qkv;     /* column-parallel: [ (h + 2 h_kv) d / tp , H ]   (flash_llama_modeling.py:220-231) */
+  B200Linear o;       /* row-parallel:    [ H, h d / tp ] */
+  B200Linear gate_up; /* column-parallel: [ 2 I / tp, H ], gate rows then up rows (:315-321) */
+  B200Linear down;    /* row-parallel:    [ H, I / tp ] */
+} B200LlamaLayer;
+
+typedef struct {
+  int32_t n_layers, hidden_size, n_heads, n_kv_heads, head_dim; /* heads are per-rank counts */
+  int32_t tp_size, tp_rank, _pad;
+  float rms_eps, softmax_scale;
+  const B200LlamaLayer* layers; /* host array [n_layers] */
+  const void* embed;            /* fp16 [vocab_rows, H]: this rank's rows of the vocab-parallel table */
+  int64_t vocab_start, vocab_rows;
+  const void* final_norm;
+  const void* lm_head; /* fp16 [vocab_rows_head, H] */
+  int64_t vocab_rows_head;
+  const void* rope_cos; /* fp16 [max_pos, d/2] (utils/layers.py:436-451) */
+  const void* rope_sin;
+} B200LlamaWeights;
+
+typedef struct {
+  int64_t T;          /* tokens in this step (decode: == B) */
+  int32_t B;          /* sequences */
+  int32_t is_prefill; /* 1: varlen causal attention over cu_seqlens; 0: paged decode attention */
+  int32_t max_s;      /* max sequence length in the batch (decode: max context incl. the new token) */
+  int32_t _pad;
+  const int64_t* input_ids;    /* [T] */
+  const int64_t* position_ids; /* [T] */
+  const int64_t* slot_mapping; /* [T] block*16+offset, <0 = padding row */
+  const int32_t* cu_seqlens;   /* [B+1] (prefill) */
+  const int32_t* block_table;  /* [B, block_table_stride] (decode) */
+  int64_t block_table_stride;
+  const int32_t* context_lens; /* [B] (decode) */
+  void* kv_pool;               /* base of [n_layers][2][num_blocks][n_kv][16][d] fp16 */
+  int64_t kv_layer_stride_bytes, kv_v_offset_bytes;
+  /* scratch, fp16 unless noted */
+  void* hidden;   /* [T, H] in: embeddings (or caller-provided inputs_embeds); out: last block output */
+  void* residual; /* [T, H] */
+  void* normed;   /* [T, H] */
+  void* qkv;      /* [T, (h + 2 h_kv) d] */
+  void* attn_out; /* [T, h d] */
+  void* gate_up;  /* [T, 2 I / tp] */
+  void* act;      /* [T, I / tp] */
+  void* attn_ws;  /* b200_attn_decode_workspace_bytes */
+  int64_t attn_ws_bytes;
+  void* gemm_ws; /* b200_gemm_workspace_bytes (max over the model's linears), first 64 KiB zeroed once */
+  /* head */
+  const int64_t* head_rows; /* optional [n_head_rows] token rows to project (lm_head_indices); NULL = all T */
+  int64_t n_head_rows;
+  void* head_in;     /* [n_head_rows, H] scratch when head_rows != NULL */
+  void* logits;      /* [rows, vocab_rows_head] fp16 */
+  int64_t* next_ids; /* optional [rows] greedy ids (single-rank only) */
+  const int64_t* banned_ids; /* optional [rows], see b200_argmax */
+} B200LlamaStep;
+
+int b200_llama_embed(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream);
+int b200_llama_attn_block(const B200LlamaWeights* w, const B200LlamaStep* s, int layer, void* stream);
+int b200_llama_mlp_block(const B200LlamaWeights* w, const B200LlamaStep* s, int layer, void* stream);
+int b200_llama_head(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream);
+int b200_llama_step(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream); /* tp_size == 1 */
 
 #ifdef __cplusplus
 }

@@ -308,9 +308,16 @@ class LlamaOracle:
         return logits, kv
 
     # -- greedy generate (Greedy chooser, utils/tokens.py:44-46) ----------------------
-    def generate_greedy(self, prompts: List[List[int]], n_new: int):
+    def generate_greedy(self, prompts: List[List[int]], n_new: int, banned_token: Optional[int] = None):
         """Returns (tokens [B, n_new], logits list per step). Mirrors FlashCausalLM.generate_token's
-        loop (models/flash_causal_lm.py:405-460): prefill then n_new-1 decode steps."""
+        loop (models/flash_causal_lm.py:405-460): prefill then n_new-1 decode steps.
+        banned_token: min_new_tokens EOS mask, `scores[idx, eos] = -inf` before the arg-max (utils/tokens.py:244-246)."""
+        def choose(lg):
+            lg = lg.float().clone()
+            if banned_token is not None:
+                lg[:, banned_token] = float("-inf")
+            return lg.argmax(-1)
+
         cu = [0]
         for p in prompts:
             cu.append(cu[-1] + len(p))
@@ -319,13 +326,13 @@ class LlamaOracle:
         logits, kv = self.forward(ids, pos, cu, None, prefill=True)
         lens = [len(p) for p in prompts]
         toks, all_logits = [], [logits]
-        nxt = logits.float().argmax(-1)
+        nxt = choose(logits)
         toks.append(nxt)
         for _ in range(n_new - 1):
             pos = torch.tensor(lens, dtype=torch.long)
             logits, kv = self.forward(nxt, pos, list(range(len(prompts) + 1)), kv, prefill=False)
             lens = [l + 1 for l in lens]
-            nxt = logits.float().argmax(-1)
+            nxt = choose(logits)
             toks.append(nxt)
             all_logits.append(logits)
         return torch.stack(toks, 1), all_logits

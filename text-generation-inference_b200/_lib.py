@@ -18,15 +18,65 @@ SIGNATURES = {
     "b200_rope_kv_write_paged": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     "b200_silu_mul": (_I, [_P, _P, _L, _L, _P]),
     "b200_embedding": (_I, [_P, _P, _P, _L, _L, _L, _L, _P]),
-    "b200_argmax": (_I, [_P, _P, _L, _L, _L, _P]),
+    "b200_argmax": (_I, [_P, _P, _L, _L, _L, _P, _P]),
+    "b200_launch_count": (_L, []),
+    "b200_timing_create": (_P, [_I]),
+    "b200_timing_destroy": (None, [_P]),
+    "b200_timing_attach": (None, [_P, _I]),
+    "b200_timing_collect": (_I, [_P, ctypes.POINTER(c_float)]),
     "b200_attn_decode_workspace_bytes": (_L, [_I, _I, _I, _I]),
     "b200_attn_decode_paged": (_I, [_P, _L, _P, _P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "b200_attn_prefill_varlen": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _P]),
     "b200_gemm_workspace_bytes": (_L, [_L, _L, _L]),
+    "b200_gemm_workspace_bytes_max": (_L, [_L, _L]),
     "b200_gemm_f16": (_I, [_P, _P, _P, _P, _L, _L, _L, _P, _P]),
     "b200_gptq_repack": (_I, [_P, _L, _L, _I, _P]),
     "b200_gemm_w4a16": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _P]),
 }
+
+
+
+class B200Linear(ctypes.Structure):
+    _fields_ = [("weight", _P), ("qweight", _P), ("qzeros", _P), ("scales", _P), ("bias", _P), ("N", _L), ("K", _L),
+                ("groupsize", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+
+
+class B200LlamaLayer(ctypes.Structure):
+    _fields_ = [("input_ln", _P), ("post_ln", _P), ("qkv", B200Linear), ("o", B200Linear), ("gate_up", B200Linear),
+                ("down", B200Linear)]
+
+
+class B200LlamaWeights(ctypes.Structure):
+    _fields_ = [("n_layers", ctypes.c_int32), ("hidden_size", ctypes.c_int32), ("n_heads", ctypes.c_int32),
+                ("n_kv_heads", ctypes.c_int32), ("head_dim", ctypes.c_int32), ("tp_size", ctypes.c_int32),
+                ("tp_rank", ctypes.c_int32), ("_pad", ctypes.c_int32), ("rms_eps", _F), ("softmax_scale", _F),
+                ("layers", ctypes.POINTER(B200LlamaLayer)), ("embed", _P), ("vocab_start", _L), ("vocab_rows", _L),
+                ("final_norm", _P), ("lm_head", _P), ("vocab_rows_head", _L), ("rope_cos", _P), ("rope_sin", _P)]
+
+
+class B200LlamaStep(ctypes.Structure):
+    _fields_ = [("T", _L), ("B", ctypes.c_int32), ("is_prefill", ctypes.c_int32), ("max_s", ctypes.c_int32),
+                ("_pad", ctypes.c_int32), ("input_ids", _P), ("position_ids", _P), ("slot_mapping", _P), ("cu_seqlens", _P),
+                ("block_table", _P), ("block_table_stride", _L), ("context_lens", _P), ("kv_pool", _P),
+                ("kv_layer_stride_bytes", _L), ("kv_v_offset_bytes", _L), ("hidden", _P), ("residual", _P), ("normed", _P),
+                ("qkv", _P), ("attn_out", _P), ("gate_up", _P), ("act", _P), ("attn_ws", _P), ("attn_ws_bytes", _L),
+                ("gemm_ws", _P), ("head_rows", _P), ("n_head_rows", _L), ("head_in", _P), ("logits", _P), ("next_ids", _P), ("banned_ids", _P)]
+
+
+_WP, _SP = ctypes.POINTER(B200LlamaWeights), ctypes.POINTER(B200LlamaStep)
+SIGNATURES.update({
+    "b200_kv_alloc_create": (_P, [ctypes.c_int32]),
+    "b200_kv_alloc_destroy": (None, [_P]),
+    "b200_kv_alloc_num_free": (ctypes.c_int32, [_P]),
+    "b200_kv_alloc_take": (_I, [_P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+    "b200_kv_alloc_release": (_I, [_P, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
+    "b200_decode_advance": (_I, [_P, _L, _P, _P, _P, _P, _P, _I, _P]),
+    "b200_llama_embed": (_I, [_WP, _SP, _P]),
+    "b200_llama_attn_block": (_I, [_WP, _SP, _I, _P]),
+    "b200_llama_mlp_block": (_I, [_WP, _SP, _I, _P]),
+    "b200_llama_head": (_I, [_WP, _SP, _P]),
+    "b200_llama_step": (_I, [_WP, _SP, _P]),
+})
 
 _lib = None
 

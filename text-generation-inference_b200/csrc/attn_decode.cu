@@ -265,13 +265,17 @@ static int launch_decode(const void* q, int64_t q_token_stride, const void* k_po
   float* part_o = (float*)workspace;
   float* part_ml = part_o + (int64_t)B * n_heads * n_chunks * D;
   dim3 grid(n_chunks, n_kv, B);
+  b200_timing_mark(B200_TIME_ATTN_DECODE, 0, st);
   attn_decode_paged_kernel<D><<<grid, kDecodeThreads, S::kBytes, st>>>(
       (const __half*)q, q_token_stride, (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o,
       part_ml, n_heads, n_kv, n_chunks, scale * 1.4426950408889634f);
+  b200_timing_mark(B200_TIME_ATTN_DECODE, 1, st);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   attn_decode_combine_kernel<D><<<dim3(n_heads, B), D, 0, st>>>(part_o, part_ml, context_lens, (__half*)out, out_token_stride,
                                                                 n_heads, n_chunks);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 

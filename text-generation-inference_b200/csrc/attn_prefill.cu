@@ -191,6 +191,7 @@ static int launch_prefill(const void* q, int64_t qs, const void* k, int64_t ks, 
   attn_prefill_varlen_kernel<D><<<grid, 128, kSmem, st>>>((const __half*)q, qs, (const __half*)k, ks, (const __half*)v, vs, cu,
                                                           (__half*)out, os, n_heads, n_kv, scale * 1.4426950408889634f, causal);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 

@@ -20,6 +20,12 @@
   } while (0)
 
 void b200_set_last_error(const char* msg);
+void b200_count_launches(int n);  // kernels of this library enqueued so far (bench.py "gpu_launches")
+// event pair around one launch of kernel family `which` when a timing handle is attached (runtime.cu)
+#define B200_TIME_ATTN_DECODE 1
+#define B200_TIME_GEMM_W4A16 2
+#define B200_TIME_GEMM_F16 3
+void b200_timing_mark(int which, int is_stop, cudaStream_t st);
 
 namespace b200 {
 

@@ -175,8 +175,10 @@ __global__ void embedding_kernel(const __half* __restrict__ table, const int64_t
 // greedy arg-max over fp16 logits (first index wins ties, like torch.argmax on a row scan)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) argmax_kernel(const __half* __restrict__ logits, int64_t* __restrict__ out, int64_t V,
-                                                       int64_t ld) {
+                                                       int64_t ld, const int64_t* __restrict__ banned) {
   const __half* row = logits + (size_t)blockIdx.x * ld;
+  // banned[row] >= 0: that token's score counts as -inf (min_new_tokens EOS mask, utils/tokens.py:244-246)
+  const int64_t ban = banned ? banned[blockIdx.x] : -1;
   float best = -INFINITY;
   int64_t best_i = 0x7fffffffffffffffLL;
   const int64_t V8 = V & ~7LL;
@@ -185,12 +187,12 @@ __global__ void __launch_bounds__(256) argmax_kernel(const __half* __restrict__ 
     const __half* hv = reinterpret_cast<const __half*>(&v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float f = __half2float(hv[j]);
+      float f = (i + j == ban) ? -INFINITY : __half2float(hv[j]);
       if (f > best || (f == best && i + j < best_i)) { best = f; best_i = i + j; }
     }
   }
   for (int64_t i = V8 + threadIdx.x; i < V; i += 256) {
-    float f = __half2float(row[i]);
+    float f = (i == ban) ? -INFINITY : __half2float(row[i]);
     if (f > best || (f == best && i < best_i)) { best = f; best_i = i; }
   }
   __shared__ float sv[8];
@@ -227,6 +229,7 @@ extern "C" int b200_rmsnorm_residual(const void* h, const void* residual, const 
   rmsnorm_residual_kernel<256><<<(unsigned)T, 256, smem, st>>>((const __half*)h, (const __half*)residual, (const __half*)gamma,
                                                                (__half*)normed_out, (__half*)residual_out, (int)H, eps);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 
@@ -247,6 +250,7 @@ extern "C" int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* 
     return B200_ERR_UNSUPPORTED;
   }
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 
@@ -258,6 +262,7 @@ extern "C" int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t 
   if (blocks > 148 * 16) blocks = 148 * 16;
   silu_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_up, (__half*)out, I, total8);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 
@@ -267,13 +272,16 @@ extern "C" int b200_embedding(const void* table, const int64_t* ids, void* out, 
   if (H % 8 != 0) { b200_set_last_error("embedding: H % 8 != 0"); return B200_ERR_ARG; }
   embedding_kernel<<<(unsigned)T, 128, 0, (cudaStream_t)stream>>>((const __half*)table, ids, (__half*)out, (int)H, vocab_start, vocab_rows);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 
-extern "C" int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, void* stream) {
+extern "C" int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, const int64_t* banned_ids,
+                           void* stream) {
   if (B == 0) return B200_OK;
   if (ld % 8 != 0) { b200_set_last_error("argmax: row stride must be a multiple of 8 halves"); return B200_ERR_ARG; }
-  argmax_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, out_ids, V, ld);
+  argmax_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, out_ids, V, ld, banned_ids);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }

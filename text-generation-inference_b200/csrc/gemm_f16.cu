@@ -190,6 +190,16 @@ extern "C" int64_t b200_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K) {
   return kCounterBytes + (splits > 1 ? (int64_t)splits * T * N * 4 : 0);
 }
 
+// upper bound of b200_gemm_workspace_bytes over every T (split-K only happens while the tile grid is small)
+extern "C" int64_t b200_gemm_workspace_bytes_max(int64_t N, int64_t K) {
+  int64_t best = kCounterBytes;
+  for (int64_t T = 1; T <= 32768; T = T < 256 ? T + 1 : T + 256) {
+    const int64_t b = b200_gemm_workspace_bytes(T, N, K);
+    if (b > best) best = b;
+  }
+  return best;
+}
+
 template <int TN>
 static int launch_gemm_f16(const CUtensorMap* mw, const CUtensorMap* mx, void* y, void* workspace, const void* bias, int T, int N,
                            int K, cudaStream_t st) {
@@ -209,9 +219,12 @@ static int launch_gemm_f16(const CUtensorMap* mw, const CUtensorMap* mx, void* y
   int* counters = (int*)workspace;
   float* partial = workspace ? (float*)((char*)workspace + kCounterBytes) : nullptr;
   dim3 grid(n_tiles_n, n_tiles_t, splits);
+  b200_timing_mark(B200_TIME_GEMM_F16, 0, st);
   gemm_f16_kernel<TN><<<grid, kGemmThreads, C::kSmemBytes, st>>>(*mw, *mx, (__half*)y, partial, counters, (const __half*)bias, T, N,
                                                                   n_kblocks, per);
+  b200_timing_mark(B200_TIME_GEMM_F16, 1, st);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 

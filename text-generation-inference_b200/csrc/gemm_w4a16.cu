@@ -280,6 +280,7 @@ extern "C" int b200_gptq_repack(void* qweight, int64_t K, int64_t N, int inverse
   if (blocks > 148 * 8) blocks = 148 * 8;
   gptq_repack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint32_t*)qweight, n_words, inverse);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 
@@ -302,10 +303,13 @@ static int launch_gemm_w4(const CUtensorMap* mq, const CUtensorMap* mx, const vo
   int* counters = (int*)workspace;
   float* partial = workspace ? (float*)((char*)workspace + kW4CounterBytes) : nullptr;
   dim3 grid(n_tiles_n, n_tiles_t, splits);
+  b200_timing_mark(B200_TIME_GEMM_W4A16, 0, st);
   gemm_w4a16_kernel<TN><<<grid, kW4Threads, C::kSmemBytes, st>>>(*mq, *mx, (const int32_t*)qzeros, (const __half*)scales, (__half*)y,
                                                                  partial, counters, (const __half*)bias, T, N, n_kblocks, per,
                                                                  groupsize);
+  b200_timing_mark(B200_TIME_GEMM_W4A16, 1, st);
   B200_CHECK_LAUNCH();
+  b200_count_launches(1);
   return B200_OK;
 }
 

@@ -12,6 +12,11 @@ static thread_local std::string g_last_error;
 
 void b200_set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void b200_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" const char* b200_last_error(void) { return g_last_error.c_str(); }
 extern "C" int b200_abi_version(void) { return 1; }
 
@@ -68,3 +73,56 @@ const CUtensorMap* get_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, ui
 }
 
 }  // namespace b200
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-kernel device timing for bench.py's roofline line: CUDA events recorded on the launching stream around
+// every launch of one chosen kernel family while a timing handle is attached.
+// ---------------------------------------------------------------------------------------------------------
+#include <vector>
+struct B200Timing {
+  std::vector<cudaEvent_t> ev;  // start/stop pairs
+  int used = 0;
+  int which = 0;
+};
+static B200Timing* g_timing = nullptr;
+
+extern "C" void* b200_timing_create(int max_launches) {
+  auto* t = new B200Timing();
+  t->ev.resize((size_t)max_launches * 2);
+  for (auto& e : t->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { b200_set_last_error("timing_create: cudaEventCreate failed"); delete t; return nullptr; }
+  return t;
+}
+extern "C" void b200_timing_destroy(void* h) {
+  auto* t = static_cast<B200Timing*>(h);
+  if (!t) return;
+  if (g_timing == t) g_timing = nullptr;
+  for (auto& e : t->ev) cudaEventDestroy(e);
+  delete t;
+}
+// which: B200_TIME_ATTN_DECODE / _GEMM_W4A16 / _GEMM_F16; h == NULL detaches
+extern "C" void b200_timing_attach(void* h, int which) {
+  g_timing = static_cast<B200Timing*>(h);
+  if (g_timing) { g_timing->which = which; g_timing->used = 0; }
+}
+// synchronises on the recorded events; returns the number of timed launches and their summed duration
+extern "C" int b200_timing_collect(void* h, float* total_ms) {
+  auto* t = static_cast<B200Timing*>(h);
+  float sum = 0.f;
+  for (int i = 0; i + 1 < t->used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(t->ev[i + 1]) != cudaSuccess || cudaEventElapsedTime(&ms, t->ev[i], t->ev[i + 1]) != cudaSuccess) {
+      b200_set_last_error("timing_collect: event query failed");
+      return -1;
+    }
+    sum += ms;
+  }
+  *total_ms = sum;
+  return t->used / 2;
+}
+void b200_timing_mark(int which, int is_stop, cudaStream_t st) {
+  B200Timing* t = g_timing;
+  if (!t || t->which != which || t->used + (is_stop ? 0 : 2) > (int)t->ev.size()) return;
+  if (!is_stop) { cudaEventRecord(t->ev[t->used], st); }
+  else if (t->used + 1 < (int)t->ev.size()) { cudaEventRecord(t->ev[t->used + 1], st); t->used += 2; }
+}

@@ -75,12 +75,13 @@ def embedding(table: torch.Tensor, ids: torch.Tensor, vocab_start: int = 0) -> t
     return out
 
 
-def argmax(logits: torch.Tensor) -> torch.Tensor:
+def argmax(logits: torch.Tensor, banned_ids: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(logits, torch.float16, "logits")
     B, V = logits.shape
     assert logits.stride(1) == 1
-    out = torch.empty(B, dtype=torch.int64, device=logits.device)
-    _lib.check(_lib.load().b200_argmax(_ptr(logits), _ptr(out), B, V, logits.stride(0), _stream()), "argmax")
+    if out is None:
+        out = torch.empty(B, dtype=torch.int64, device=logits.device)
+    _lib.check(_lib.load().b200_argmax(_ptr(logits), _ptr(out), B, V, logits.stride(0), _ptr(banned_ids), _stream()), "argmax")
     return out
 
 
@@ -129,7 +130,7 @@ _gemm_ws = {}
 
 def gemm_workspace(device, T: int, N: int, K: int) -> torch.Tensor:
     """Per-device split-K workspace (counters zeroed once; the kernels re-arm them)."""
-    need = _lib.load().b200_gemm_workspace_bytes(T, N, K)
+    need = _lib.load().b200_gemm_workspace_bytes_max(N, K)
     ws = _gemm_ws.get(device)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)

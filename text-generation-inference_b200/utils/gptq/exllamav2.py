@@ -1,0 +1,64 @@
+"""GPTQ int4 linear on the tcgen05 in-kernel-dequant GEMM.
+
+Mirrors /root/reference/server/text_generation_server/utils/gptq/exllamav2.py:100-144 (`Ex4bitLinearV2`: same
+constructor arguments, `post_init()` one-time repack, `forward`), with `exllamav2_kernels.make_q_matrix` /
+`gemm_half_q_half` replaced by `b200_gptq_repack` / `b200_gemm_w4a16`.  No scratch `temp_dq`: the kernel never
+materialises the fp16 matrix (contrast :65-97, :87).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import _ops
+
+
+class Ex4bitLinearV2(nn.Module):
+    QUANT_TYPE = "exllamav2"
+
+    def __init__(self, qweight, qzeros, scales, g_idx, bias, bits, groupsize):
+        super().__init__()
+        assert bits == 4, "b200 GPTQ kernel supports 4-bit only"  # exllamav2.py:105
+        self.q_handle = None
+        self.qweight = qweight
+        self.qzeros = qzeros
+        self.scales = scales.to(torch.float16)
+        self.g_idx = g_idx
+        self.bias = bias if bias is not None else None
+        self.group_size = groupsize
+        self.infeatures = self.qweight.shape[0] // bits * 32
+        self.outfeatures = self.qweight.shape[1]
+        self.height = self.infeatures
+        self.width = self.outfeatures
+        assert self.infeatures % 32 == 0 and self.outfeatures % 32 == 0  # exllamav2.py:118-119
+        if g_idx is not None and groupsize > 0:
+            trivial = torch.equal(g_idx.cpu().to(torch.int64), torch.arange(self.infeatures) // groupsize)
+            if not trivial and not bool((g_idx == 0).all()):
+                raise NotImplementedError("act-order (non-trivial g_idx) checkpoints are not supported yet")
+
+    def post_init(self, temp_dq=None):
+        """exllamav2.py:124-137: one-time in-place weight shuffle."""
+        assert self.qweight.device.type == "cuda"
+        if self.q_handle is None:
+            self.qweight = self.qweight.contiguous()
+            _ops().gptq_repack(self.qweight)
+            self.qzeros = self.qzeros.contiguous()
+            self.scales = self.scales.contiguous()
+            self.q_handle = True
+
+    def forward(self, x, force_cuda=False):
+        if self.q_handle is None:
+            self.post_init()
+        out_shape = x.shape[:-1] + (self.outfeatures,)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        out = _ops().gemm_w4a16(x2, self.qweight, self.qzeros, self.scales, self.group_size, self.bias)
+        return out.view(out_shape)
+
+    def temp_dq_size(self):
+        return 0
+
+    def temp_fwd_size(self, max_input_len, max_batch_size):
+        return 0
+
+    def scratch_space_fixed(self, max_input_len=4096, max_batch_size=16):
+        return 0
