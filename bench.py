@@ -43,7 +43,7 @@ WORKLOADS = {
     "llama2-7b-fp16": ("llama-2-7b", None, 64, 1024, 2048),
     "tinyllama-fp16": ("tinyllama-1.1b", None, 32, 512, 1024),
     "llama3-8b-gptq": ("llama-3-8b", "gptq", 64, 1024, 2048),
-    "tiny-test": ("tiny-test", None, 4, 32, 64),
+    "tiny-test": ("tiny-test", None, 4, 32, 256),
 }
 METRIC = "decode_tokens_per_s"
 UNIT = "tokens/s"
@@ -240,8 +240,8 @@ def run_gpu(args, workload):
         st = batch._fused
         kv = batch.past_key_values
 
-        def device_step():
-            model._run_fused_step(batch, st)
+        def device_step(use_graph=True):
+            model._run_fused_step(batch, st, use_graph)
             batch.position_ids += 1
             batch.input_ids.copy_(st["next_ids"])
 
@@ -251,20 +251,19 @@ def run_gpu(args, workload):
         timing = lib.b200_timing_create(K * cfg.num_hidden_layers + 8)
         # eager steps carry the per-kernel events; graph replays cannot (events are not captured), so the roofline
         # pass runs the same K steps eagerly first, then the headline pass replays the graph
-        graph = st["graph"]
-        st["graph"] = None
         lib.b200_timing_attach(timing, 1)
         barrier()
         for _ in range(K):
-            device_step()
+            device_step(use_graph=False)
         barrier()
         lib.b200_timing_attach(None, 0)
         tot = ctypes.c_float(0)
         n_timed = lib.b200_timing_collect(timing, ctypes.byref(tot))
+        if n_timed < 0:
+            raise RuntimeError(lib.b200_last_error().decode())
         attn_ms = tot.value / max(n_timed, 1)
         ctx_roof = cur + (K + 1) / 2.0  # mean context (incl. the token written) over those K steps
         cur += K
-        st["graph"] = graph
         # headline pass
         sampler = ClockSampler(torch.cuda.current_device())
         sampler.start()
@@ -312,10 +311,7 @@ def run_gpu(args, workload):
     # graph replays launch the same kernels as an eager step; count them from one eager step's counter delta
     l0 = lib.b200_launch_count()
     with torch.inference_mode():
-        g = st["graph"]
-        st["graph"] = None
-        device_step()
-        st["graph"] = g
+        device_step(use_graph=False)
         torch.cuda.synchronize()
     launches_per_step = lib.b200_launch_count() - l0
 

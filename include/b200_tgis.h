@@ -28,6 +28,7 @@ extern "C" {
 
 int b200_abi_version(void);
 const char* b200_last_error(void);
+const char* b200_cuda_peek_error(void); /* debug: pending CUDA runtime error string, not cleared */
 /* number of kernels this library has enqueued in this process (bench.py reports the delta as "gpu_launches") */
 int64_t b200_launch_count(void);
 

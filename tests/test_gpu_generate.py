@@ -62,14 +62,27 @@ def _prompts(seed, lens, vocab):
 
 
 def _oracle_tokens(oracle, prompts, n_new):
+    """-> (tokens [B, n_new], n_exact [B]): per sequence, the number of leading steps whose oracle top-2 gap exceeds
+    2 fp16 ulp — up to there the ids must match exactly; past a near-tie the trajectories may legitimately fork."""
     toks, logits = oracle.generate_greedy(prompts, n_new, banned_token=EOS)
-    # assert the case is decisive (outside the 2-ulp tie band) so exact equality is the right bar
-    for lg in logits:
+    n_exact = [n_new] * len(prompts)
+    for step, lg in enumerate(logits):
         l = lg.float().clone()
         l[:, EOS] = float("-inf")
         top2 = l.topk(2, -1).values
-        assert ((top2[:, 0] - top2[:, 1]) > 2 * top2[:, 0].abs().clamp(min=1.0) * 2.0 ** -10).all(), "test case inside the tie band"
-    return toks
+        decisive = (top2[:, 0] - top2[:, 1]) > 2 * top2[:, 0].abs().clamp(min=1.0) * 2.0 ** -10
+        for b in range(len(prompts)):
+            if not decisive[b]:
+                n_exact[b] = min(n_exact[b], step)
+    return toks, n_exact
+
+
+def _assert_prefix_equal(got, ref, n_exact, min_total):
+    total = 0
+    for b, n in enumerate(n_exact):
+        assert list(got[b][:n]) == list(ref[b][:n]), f"sequence {b}: {got[b]} vs oracle {list(ref[b])} (exact for {n} steps)"
+        total += n
+    assert total >= min_total, f"test case too weak: only {total} decisive tokens"
 
 
 @pytest.mark.parametrize("quantize", [None, "gptq"])
@@ -77,7 +90,7 @@ def test_generate_token_matches_oracle(tmp_path, quantize):
     model, oracle, tok = _setup(tmp_path, quantize)
     n_new = 12
     prompts = _prompts(1, [7, 33, 16, 1], 512)
-    ref = _oracle_tokens(oracle, prompts, n_new)
+    ref, n_exact = _oracle_tokens(oracle, prompts, n_new)
     with torch.inference_mode():
         batch, errs = model.batch_type.from_pb(_pb_batch(0, prompts, n_new), tok, torch.float16, model.device, None, None, True)
         assert not errs and len(batch) == 4
@@ -90,10 +103,10 @@ def test_generate_token_matches_oracle(tmp_path, quantize):
             assert out[1] is None and not out[2]
             for t in out[0]:
                 got[t.request_id].append(t.token_id)
-    assert torch.tensor(got).tolist() == ref.tolist()
+    _assert_prefix_equal(got, ref.tolist(), n_exact, min_total=24)
     # all_input_ids_tensor holds prompt + generated tokens (flash_causal_lm.py:533-535)
     for i, p in enumerate(prompts):
-        assert batch.all_input_ids_tensor[i, :len(p) + n_new].tolist() == p + ref[i].tolist()
+        assert batch.all_input_ids_tensor[i, :len(p) + n_new].tolist() == p + got[i]
     model.kv_cache_manager.free_sequences(batch.sequence_ids)
     assert model.kv_cache_manager.free_blocks == model.kv_cache_manager.total_num_gpu_blocks
 
@@ -103,7 +116,7 @@ def test_generate_token_general_chooser_path_matches_fused(tmp_path):
     model, oracle, tok = _setup(tmp_path, None)
     n_new = 6
     prompts = _prompts(2, [9, 20], 512)
-    ref = _oracle_tokens(oracle, prompts, n_new)
+    ref, n_exact = _oracle_tokens(oracle, prompts, n_new)
     with torch.inference_mode():
         batch, _ = model.batch_type.from_pb(_pb_batch(0, prompts, n_new, logprobs=True), tok, torch.float16, model.device, None, None, True)
         got = [[] for _ in prompts]
@@ -115,7 +128,7 @@ def test_generate_token_general_chooser_path_matches_fused(tmp_path):
             toks = model.generate_token(batch)[0]
         for t in toks:
             got[t.request_id].append(t.token_id)
-    assert got == ref.tolist()
+    _assert_prefix_equal(got, ref.tolist(), n_exact, min_total=6)
 
 
 def test_concatenate_and_prune_are_kv_free_and_exact(tmp_path):
@@ -125,7 +138,10 @@ def test_concatenate_and_prune_are_kv_free_and_exact(tmp_path):
     mgr = model.kv_cache_manager
     n_new = 10
     pa, pbs = _prompts(3, [12, 5], 512), _prompts(4, [20, 3], 512)
-    ref = {i: _oracle_tokens(oracle, [p], n_new)[0].tolist() for i, p in enumerate(pa + pbs)}
+    ref, n_ex = {}, {}
+    for i, p in enumerate(pa + pbs):
+        t, ne = _oracle_tokens(oracle, [p], n_new)
+        ref[i], n_ex[i] = t[0].tolist(), ne[0]
     got = {i: [] for i in range(4)}
 
     def take(out):
@@ -156,6 +172,8 @@ def test_concatenate_and_prune_are_kv_free_and_exact(tmp_path):
             take(model.generate_token(C))
         assert model.batch_type.prune(C, [r.id for r in C.requests]) is None
     for i in (0, 2, 3):
-        assert got[i][:n_new] == ref[i], f"request {i}"
-    assert got[1] == ref[1][:len(got[1])]
+        assert got[i][:n_ex[i]] == ref[i][:n_ex[i]], f"request {i}: {got[i]} vs {ref[i]}"
+    n1 = min(len(got[1]), n_ex[1])
+    assert got[1][:n1] == ref[1][:n1]
+    assert sum(n_ex.values()) >= 20, "test case too weak"
     assert mgr.free_blocks == mgr.total_num_gpu_blocks, "every block returned after all requests finished"

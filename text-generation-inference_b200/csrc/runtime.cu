@@ -18,6 +18,8 @@ void b200_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_rela
 extern "C" int64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* b200_last_error(void) { return g_last_error.c_str(); }
+// debug aid: pending CUDA runtime error of this library's runtime instance (does not clear it)
+extern "C" const char* b200_cuda_peek_error(void) { return cudaGetErrorString(cudaPeekAtLastError()); }
 extern "C" int b200_abi_version(void) { return 1; }
 
 namespace b200 {
@@ -111,8 +113,13 @@ extern "C" int b200_timing_collect(void* h, float* total_ms) {
   float sum = 0.f;
   for (int i = 0; i + 1 < t->used; i += 2) {
     float ms = 0.f;
-    if (cudaEventSynchronize(t->ev[i + 1]) != cudaSuccess || cudaEventElapsedTime(&ms, t->ev[i], t->ev[i + 1]) != cudaSuccess) {
-      b200_set_last_error("timing_collect: event query failed");
+    cudaError_t e1 = cudaEventSynchronize(t->ev[i + 1]);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaEventElapsedTime(&ms, t->ev[i], t->ev[i + 1]) : e1;
+    if (e2 != cudaSuccess) {
+      char buf[128];
+      snprintf(buf, sizeof(buf), "timing_collect: pair %d failed: %s", i / 2, cudaGetErrorString(e2));
+      b200_set_last_error(buf);
+      cudaGetLastError();
       return -1;
     }
     sum += ms;

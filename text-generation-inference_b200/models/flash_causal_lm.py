@@ -320,13 +320,13 @@ class FlashCausalLM(Model):
         st["steps"] += 1
         return generated, [], forward_time_ns
 
-    def _run_fused_step(self, batch, st) -> None:
+    def _run_fused_step(self, batch, st, use_graph: bool = True) -> None:
         """decode_advance (+ device-to-device token chaining) and the whole model step; replayed as a CUDA graph from
         the third step of a stable batch on."""
         kv, B = batch.past_key_values, len(batch)
         lib = _lib.load()
         s = st["step"]
-        if st["graph"] is not None:
+        if use_graph and st["graph"] is not None:
             st["graph"].replay()
             return
 
@@ -345,7 +345,7 @@ class FlashCausalLM(Model):
                 else:
                     ops.argmax(st["logits"], st["banned"], out=st["next_ids"])
 
-        if st["steps"] >= 2 and USE_CUDA_GRAPHS:
+        if use_graph and st["steps"] >= 2 and USE_CUDA_GRAPHS:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 enqueue()
