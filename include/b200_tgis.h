@@ -29,6 +29,8 @@ extern "C" {
 int b200_abi_version(void);
 const char* b200_last_error(void);
 const char* b200_cuda_peek_error(void); /* debug: pending CUDA runtime error string, not cleared */
+void b200_debug_w4_flags(int flags); /* debug: timing experiments (results invalid): 1 no scale/zero TMA, 2 no activation TMA, 4 one MMA per unit */
+void b200_debug_w4_trace(void* device_buffer); /* debug: [n_ctas][64] u64 phase timestamps of int4 GEMM launches; NULL = off */
 /* number of kernels this library has enqueued in this process (bench.py reports the delta as "gpu_launches") */
 int64_t b200_launch_count(void);
 

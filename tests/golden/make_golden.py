@@ -163,6 +163,9 @@ class _Group:
 
 def gold_weights(weights_mod, tmpdir):
     from safetensors.torch import save_file
+    # the exllama (GPTQ CUDA) branch of get_multi_weights_row is the hot path; without the un-vendored kernels the
+    # module-level flag is False and the loader would take the Triton branch (full scales/zeros + sharded g_idx)
+    sys.modules["text_generation_server.utils.layers"].HAS_GPTQ_CUDA = True
     cfg = oll.LlamaConfig(256, 512, 1, 4, 2, 512)
     out = {}
     for quant in (None, "gptq"):

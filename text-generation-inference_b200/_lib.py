@@ -15,6 +15,8 @@ SIGNATURES = {
     "b200_abi_version": (_I, []),
     "b200_last_error": (c_char_p, []),
     "b200_cuda_peek_error": (c_char_p, []),
+    "b200_debug_w4_trace": (None, [_P]),
+    "b200_debug_w4_flags": (None, [_I]),
     "b200_rmsnorm_residual": (_I, [_P, _P, _P, _P, _P, _L, _L, _F, _P]),
     "b200_rope_kv_write_paged": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     "b200_silu_mul": (_I, [_P, _P, _L, _L, _P]),

@@ -145,13 +145,36 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     if (s_is_last) {
       __threadfence();
       const int t_hi = min(T, t0 + TN);
-      for (int idx = threadIdx.x; idx < (t_hi - t0) * kTileM; idx += kGemmThreads) {
-        const int t = t0 + idx / kTileM, n = n0 + idx % kTileM;
-        if (n < N) {
-          float acc = 0.f;
-          for (int s = 0; s < n_splits; ++s) acc += __ldcg(&partial[((size_t)s * T + t) * N + n]);
-          if (bias) acc += __half2float(bias[n]);
-          y[(size_t)t * N + n] = __float2half_rn(acc);
+      if ((N & 3) == 0) {
+        // float4 per thread, all split loads of an element in flight together (latency-bound otherwise)
+        for (int idx = threadIdx.x; idx < (t_hi - t0) * (kTileM / 4); idx += kGemmThreads) {
+          const int t = t0 + idx / (kTileM / 4), n = n0 + (idx % (kTileM / 4)) * 4;
+          if (n < N) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int s = 0; s < n_splits; ++s) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(&partial[((size_t)s * T + t) * N + n]));
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            if (bias) {
+              acc.x += __half2float(bias[n]); acc.y += __half2float(bias[n + 1]);
+              acc.z += __half2float(bias[n + 2]); acc.w += __half2float(bias[n + 3]);
+            }
+            uint2 o;
+            o.x = pack_half2(acc.x, acc.y);
+            o.y = pack_half2(acc.z, acc.w);
+            *reinterpret_cast<uint2*>(&y[(size_t)t * N + n]) = o;
+          }
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < (t_hi - t0) * kTileM; idx += kGemmThreads) {
+          const int t = t0 + idx / kTileM, n = n0 + idx % kTileM;
+          if (n < N) {
+            float acc = 0.f;
+            for (int s = 0; s < n_splits; ++s) acc += __ldcg(&partial[((size_t)s * T + t) * N + n]);
+            if (bias) acc += __half2float(bias[n]);
+            y[(size_t)t * N + n] = __float2half_rn(acc);
+          }
         }
       }
     }
@@ -183,11 +206,15 @@ static int pick_tn(int64_t T) { return T <= 16 ? 16 : T <= 32 ? 32 : T <= 64 ? 6
 // Workspace layout shared by both GEMMs: [tile counters, kCounterBytes][fp32 split-K partials].
 constexpr int64_t kCounterBytes = 64 * 1024;
 
+int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K);  // gemm_w4a16.cu (stream-K partials)
+
 extern "C" int64_t b200_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K) {
   const int TN = pick_tn(T);
   const int n_tiles = (int)(((N + kTileM - 1) / kTileM) * ((T + TN - 1) / TN));
   const int splits = b200_pick_splits(n_tiles, (int)((K + kTileK - 1) / kTileK));
-  return kCounterBytes + (splits > 1 ? (int64_t)splits * T * N * 4 : 0);
+  const int64_t f16 = splits > 1 ? (int64_t)splits * T * N * 4 : 0;
+  const int64_t w4 = b200_w4_partial_bytes(T, N, K);
+  return kCounterBytes + (f16 > w4 ? f16 : w4);
 }
 
 // upper bound of b200_gemm_workspace_bytes over every T (split-K only happens while the tile grid is small)
