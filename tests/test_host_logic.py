@@ -1,0 +1,209 @@
+"""CPU tests of the host-side runtime around the hot path: batch construction from the wire message, the paged KV
+manager, prune / concatenate bookkeeping (block-table edits only), `get_indices_to_keep`, and the world-size-2
+tensor-parallel host logic over gloo (shard loading + collective placement)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import llama as oll
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import __graft_entry__ as ge
+    ge._load_build_module().build()
+    import tgis_b200  # noqa: F401
+    from tgis_b200 import pb
+    from tgis_b200.models.flash_causal_lm import FlashCausalLMBatch
+    from tgis_b200.models.model import Model
+    from tgis_b200.utils.paged import OutOfBlocks, PagedKVCacheManager, PagedKVState
+    from tgis_b200.utils.synthetic import make_tokenizer
+    return dict(pb=pb, Batch=FlashCausalLMBatch, Model=Model, Mgr=PagedKVCacheManager, State=PagedKVState,
+                OutOfBlocks=OutOfBlocks, tok=make_tokenizer(64))
+
+
+def _req(pb, i, text, n_in, n_out, truncate=False, **params):
+    return pb.Request(id=i, inputs=text, input_length=n_in, truncate=truncate, max_output_length=n_out,
+                      parameters=pb.NextTokenChooserParameters(temperature=0.0, top_p=1.0, **params))
+
+
+def test_from_pb_builds_the_ragged_batch(mods):
+    pb, Batch, tok = mods["pb"], mods["Batch"], mods["tok"]
+    msg = pb.Batch(id=11, requests=[_req(pb, 0, "test <tok5> test", 3, 4), _req(pb, 1, "test " * 100, 5, 2, truncate=True),
+                                    _req(pb, 2, "<tok9>", 1, 6)])
+    b, errs = Batch.from_pb(msg, tok, torch.float16, torch.device("cpu"), None, None, True)
+    assert not errs and len(b) == 3 and b.get_id() == 11
+    assert b.input_ids.tolist() == [3, 5, 3, 3, 3, 3, 3, 3, 9]
+    assert b.position_ids.tolist() == [0, 1, 2, 0, 1, 2, 3, 4, 0]
+    assert b.cu_seqlens.tolist() == [0, 3, 8, 9] and b.cu_seqlens.dtype == torch.int32
+    assert b.input_lengths == [3, 5, 1] and b.total_lengths == [7, 7, 7] and b.max_seqlen == 5
+    assert b.all_input_ids_tensor.shape == (3, 7)
+    assert b.all_input_ids_tensor[1].tolist() == [3, 3, 3, 3, 3, 0, 0]  # padded with pad_token_id
+    assert b.past_key_values is None and b.sequence_ids == []
+    assert b.next_token_chooser.is_plain_greedy
+
+
+def test_from_pb_reports_prefix_requests_as_errors(mods):
+    pb, Batch, tok = mods["pb"], mods["Batch"], mods["tok"]
+    r = _req(pb, 4, "test", 1, 2)
+    r.prefix_id = "some-prefix"
+    b, errs = Batch.from_pb(pb.Batch(id=1, requests=[r]), tok, torch.float16, torch.device("cpu"), None, None, True)
+    assert b is None and len(errs) == 1 and errs[0].request_id == 4
+
+
+def test_get_indices_to_keep_matches_reference_semantics(mods):
+    Model, pb = mods["Model"], mods["pb"]
+    reqs = [pb.Request(id=i) for i in (2, 5, 7, 9, 12)]
+    assert Model.get_indices_to_keep(reqs, [5, 9]) == [0, 2, 4]
+    assert Model.get_indices_to_keep(reqs, [2, 5, 7, 9, 12]) == []
+    assert Model.get_indices_to_keep(reqs, [1, 3, 12]) == [0, 1, 2, 3]  # ids not in the batch are skipped
+
+
+def test_paged_kv_manager_allocation_and_exhaustion(mods):
+    Mgr, OutOfBlocks = mods["Mgr"], mods["OutOfBlocks"]
+    m = Mgr(num_layers=2, num_heads=4, emb_dim=256, kv_heads=2, device="cpu", total_num_gpu_blocks=10)
+    assert m.pool.shape == (2, 2, 10, 2, 16, 64) and m.free_blocks == 10
+    assert m.block_bytes() == 2 * 2 * 2 * 16 * 64 * 2
+    s = m.allocate_tokens([17, 1], reserve_tokens=[15, 15])      # 32 -> 2 blocks, 16 -> 1 block
+    assert [len(m.sequence_blocks(i)) for i in s] == [2, 1] and m.free_blocks == 7
+    assert m.slot_mapping_for(s, [0, 0], [17, 1]).tolist() == [b * 16 + o for b, o in
+                                                              [(m.sequence_blocks(s[0])[i // 16], i % 16) for i in range(17)]] + \
+        [m.sequence_blocks(s[1])[0] * 16]
+    bt = m.block_table_tensor(s)
+    assert bt.shape == (2, 2) and bt.dtype == torch.int32 and bt[1, 1].item() == 0
+    with pytest.raises(OutOfBlocks):
+        m.allocate_tokens([16 * 8])                               # all or nothing
+    assert m.free_blocks == 7
+    for _ in range(15):
+        assert not m.note_decode_step([s[1]])                     # inside the reservation
+    assert m.note_decode_step([s[1]]) and m.free_blocks == 6      # 17th token needs a new block
+    m.free_sequences(s)
+    assert m.free_blocks == 10
+    with pytest.raises(ValueError):
+        Mgr(num_layers=1, num_heads=4, emb_dim=256, kv_heads=2, tensor_parallel_size=4, device="cpu", total_num_gpu_blocks=2)
+
+
+def _decoding_batch(mods, batch_id, first_id, lens, n_out, mgr):
+    """a batch as generate_token(first=True) leaves it, without running a model"""
+    pb, Batch, tok, State = mods["pb"], mods["Batch"], mods["tok"], mods["State"]
+    msg = pb.Batch(id=batch_id, requests=[_req(pb, first_id + i, "test " * L, L, n_out, min_new_tokens=n_out) for i, L in enumerate(lens)])
+    b, _ = Batch.from_pb(msg, tok, torch.float16, torch.device("cpu"), None, None, True)
+    sids = mgr.allocate_tokens(lens, reserve_tokens=[n_out] * len(lens))
+    b.past_key_values = State(sids, mgr.block_table_tensor(sids), torch.tensor(lens, dtype=torch.int32),
+                              torch.empty(len(lens), dtype=torch.int64), 0)
+    b.kv_cache_manager = mgr
+    b.position_ids = torch.tensor(lens)
+    b.input_ids = torch.full((len(lens),), 3)
+    b.cu_seqlens_q = torch.arange(len(lens) + 1, dtype=torch.int32)
+    b.input_lengths = [L + 1 for L in lens]
+    b.max_seqlen += 1
+    b.cu_seqlens = b.cu_seqlens + b.cu_seqlens_q
+    return b
+
+
+def test_concatenate_and_prune_edit_block_tables_only(mods):
+    Batch, Mgr = mods["Batch"], mods["Mgr"]
+    mgr = Mgr(num_layers=1, num_heads=2, emb_dim=128, kv_heads=2, device="cpu", total_num_gpu_blocks=64)
+    a = _decoding_batch(mods, 0, 0, [5, 40], 8, mgr)
+    b = _decoding_batch(mods, 1, 2, [17], 30, mgr)
+    used = mgr.total_num_gpu_blocks - mgr.free_blocks
+    pool_before = mgr.pool.clone()
+    rows_a, rows_b = a.past_key_values.block_table.clone(), b.past_key_values.block_table.clone()
+    c = Batch.concatenate([a, b])
+    assert torch.equal(mgr.pool, pool_before) and mgr.total_num_gpu_blocks - mgr.free_blocks == used
+    assert len(c) == 3 and c.batch_id == 0 and [r.id for r in c.requests] == [0, 1, 2]
+    kv = c.past_key_values
+    assert kv.block_table.shape == (3, 3) and kv.context_lens.tolist() == [5, 40, 17]
+    assert torch.equal(kv.block_table[:2, :rows_a.shape[1]], rows_a) and torch.equal(kv.block_table[2, :rows_b.shape[1]], rows_b[0])
+    assert c.cu_seqlens.tolist() == [0, 6, 47, 65] and c.cu_seqlens_q.tolist() == [0, 1, 2, 3]
+    assert c.input_lengths == [6, 41, 18] and c.max_seqlen == 41 and c.all_input_ids_tensor.shape == (3, 48)
+    assert a.past_key_values is None and b.past_key_values is None  # inputs released (flash_causal_lm.py:246)
+    lens_before = list(c.input_lengths)
+    c = Batch.concatenate([c])                                        # concatenate([single]) is legal
+    assert c.input_lengths == lens_before and c.past_key_values.context_lens.tolist() == [5, 40, 17]
+    # prune the middle request: its blocks come back, the survivors' rows are untouched
+    seq1_blocks = list(mgr.sequence_blocks(c.past_key_values.sequence_ids[1]))
+    free_before = mgr.free_blocks
+    p = Batch.prune(c, [1])
+    assert p is c and len(p) == 2 and [r.id for r in p.requests] == [0, 2]
+    assert mgr.free_blocks == free_before + len(seq1_blocks)
+    assert p.past_key_values.context_lens.tolist() == [5, 17] and p.input_lengths == [6, 18]
+    assert p.cu_seqlens.tolist() == [0, 6, 24] and p.cu_seqlens_q.tolist() == [0, 1, 2]
+    assert p.next_token_chooser.min_new_tokens == [8, 30]
+    assert Batch.prune(p, []) is p
+    assert Batch.prune(p, [0, 2]) is None and mgr.free_blocks == mgr.total_num_gpu_blocks
+
+
+# ---------------------------------------------------------------------------------------------- world size 2 over gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _tp_worker(rank, world, port, path, quant, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import tgis_b200  # noqa: F401
+    from tgis_b200.utils.dist import initialize_torch_distributed
+    from tgis_b200.utils.weights import Weights
+    pg = initialize_torch_distributed(world, rank)        # gloo on CPU (utils/dist.py:81-83)
+    w = Weights([path], device="cpu", dtype=torch.float16, process_group=pg)
+    if quant:
+        w.gptq_bits, w.gptq_groupsize = 4, 128
+    cfg = oll.LlamaConfig(256, 512, 1, 4, 2, 512)
+    p = "model.layers.0"
+    col = w.get_multi_weights_col([f"{p}.mlp.gate_proj", f"{p}.mlp.up_proj"], quant, 0)
+    row = w.get_multi_weights_row(f"{p}.mlp.down_proj", quant)
+    if quant:
+        gate_up = oll.Linear(qweight=col[0], qzeros=col[1], scales=col[2], g_idx=col[3], groupsize=128)
+        down = oll.Linear(qweight=row[0], qzeros=row[1], scales=row[2], g_idx=row[3], groupsize=128)
+    else:
+        gate_up, down = oll.Linear(weight=col), oll.Linear(weight=row)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, cfg.hidden_size, generator=g).half()
+    part = down(oll.silu_mul(gate_up(x), cfg.intermediate_size // world)).float()
+    dist.all_reduce(part)                                  # row-parallel all-reduce (utils/layers.py:318-322)
+    # vocab-parallel embedding: out-of-shard ids contribute zeros, then all-reduce (utils/layers.py:346-357)
+    emb = w.get_partial_sharded("model.embed_tokens.weight", dim=0)
+    ids = torch.tensor([0, 255, 256, 511])
+    block = cfg.vocab_size // world
+    local = ids - rank * block
+    ok = (local >= 0) & (local < block)
+    e = torch.zeros(4, cfg.hidden_size)
+    e[ok] = emb[local[ok]].float()
+    dist.all_reduce(e)
+    if rank == 0:
+        out_q.put((part, e))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("quant", [None, "gptq"])
+def test_world_size_2_sharded_mlp_and_embedding_over_gloo(tmp_path, quant):
+    from safetensors.torch import save_file
+    cfg = oll.LlamaConfig(256, 512, 1, 4, 2, 512)
+    sd = oll.make_state_dict(cfg, seed=8, quantize=quant)
+    path = os.path.join(str(tmp_path), "m.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tp_worker, args=(r, 2, port, path, quant, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    part, e = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = oll.build_shards(cfg, sd, 1)[0].layers[0]
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, cfg.hidden_size, generator=g).half()
+    ref = full.down(oll.silu_mul(full.gate_up(x), cfg.intermediate_size)).float()
+    assert (part - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 1e-3   # fp16 partial sums vs one fp32 accumulation
+    assert torch.equal(e, sd["model.embed_tokens.weight"][[0, 255, 256, 511]].float())
