@@ -1,0 +1,86 @@
+"""GPU test (needs >= 2 GPUs; skipped otherwise): tensor-parallel FlashLlama over NCCL, one process per GPU, against the
+single-shard CPU oracle — heads and MLP columns sharded, all-reduce after o_proj / down_proj / embedding, vocab-sharded
+head gathered.  Greedy ids must agree outside the 2-ulp tie band; every rank must produce the same ids
+(lock-step shards, router/client/src/sharded_client.rs:38-48)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import llama as oll
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, path, quantize, prompts, n_new, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import tgis_b200  # noqa: F401
+    from tgis_b200.inference_engine import InferenceEngine
+    from tgis_b200.models.flash_causal_lm import FlashCausalLM
+    from tgis_b200.utils.synthetic import llama_config, make_tokenizer
+    from tests.test_gpu_generate import _pb_batch
+
+    cfg = llama_config("tiny-test", quantize=quantize, max_position_embeddings=256)
+    tok = make_tokenizer(cfg.vocab_size)
+    engine = InferenceEngine(os.path.dirname(path), None, torch.float16, quantize, cfg, 256, tokenizer=tok)
+    model = FlashCausalLM(os.path.dirname(path), None, "tgis_native", torch.float16, quantize, cfg, engine=engine, num_kv_blocks=64)
+    got = [[] for _ in prompts]
+    with torch.inference_mode():
+        batch, _ = model.batch_type.from_pb(_pb_batch(0, prompts, n_new), tok, torch.float16, model.device, None, None, True)
+        out = model.generate_token(batch, first=True)
+        for _ in range(n_new - 1):
+            for t in out[0]:
+                got[t.request_id].append(t.token_id)
+            out = model.generate_token(batch)
+        for t in out[0]:
+            got[t.request_id].append(t.token_id)
+    torch.cuda.synchronize()
+    q.put((rank, got))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("quantize", [None, "gptq"])
+def test_tp2_generate_matches_oracle(tmp_path, quantize):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from safetensors.torch import save_file
+    from tests.test_gpu_generate import _oracle_tokens, _prompts
+    # tiny-test: 4 heads / 2 kv heads / I = 512 -> tp = 2 keeps 1 kv head and 256 = 2 groups of 128 per rank
+    ocfg = oll.LlamaConfig(256, 512, 2, 4, 2, 512, 1e-5, 10000.0)
+    sd = oll.make_state_dict(ocfg, seed=99, quantize=quantize, std=0.08)
+    path = os.path.join(str(tmp_path), "model.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    if quantize:
+        import json
+        json.dump({"bits": 4, "group_size": 128}, open(os.path.join(str(tmp_path), "quantize_config.json"), "w"))
+    oracle = oll.LlamaOracle(oll.build_shards(ocfg, sd, 2))  # the oracle's own tp = 2 restatement (fp16 partial sums)
+    prompts = _prompts(5, [9, 20, 3], 512)
+    n_new = 8
+    ref, n_exact = _oracle_tokens(oracle, prompts, n_new)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, path, quantize, prompts, n_new, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res[0] == res[1], "ranks diverged"
+    total = 0
+    for b, n in enumerate(n_exact):
+        assert res[0][b][:n] == ref[b].tolist()[:n], f"sequence {b}: {res[0][b]} vs oracle {ref[b].tolist()}"
+        total += n
+    assert total >= 12
