@@ -337,7 +337,115 @@ def main():
         gold_weights(weights_mod, tmp)
         gold_flash_llama(layers, weights_mod, tmp)
     gold_chooser(my_pb)
+    gold_batch(my_pb)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--batch-only" not in sys.argv:
     main()
+
+
+# ----------------------------------------------------------------------------------------------------------
+def gold_batch(my_pb):
+    """FlashCausalLMBatch.from_pb / FlashCausalLM.generate_token / prune / concatenate of the REFERENCE, on CPU, with a
+    stand-in `model.forward` (deterministic logits from the token ids; KV tensors of the reference's contiguous layout):
+    pins the host-side batch bookkeeping (ids, positions, cu_seqlens, all_input_ids_tensor, lengths, chooser counters)
+    through prefill, decode steps, an add-on batch + concatenate, and a prune.  -> batch_bookkeeping.npz"""
+    import tgis_b200  # noqa: F401
+    from tgis_b200.utils.synthetic import make_tokenizer
+    for name, rel in (("dist", "utils/dist.py"), ("token_types", "utils/token_types.py"), ("layers", "utils/layers.py")):
+        if f"text_generation_server.utils.{name}" not in sys.modules:
+            _load(f"text_generation_server.utils.{name}", rel)
+    _pkg("text_generation_server.inference_engine", os.path.join(REF, "inference_engine"))
+    sys.modules["text_generation_server.inference_engine"].get_inference_engine_class = lambda name: None
+    _load("text_generation_server.inference_engine.engine", "inference_engine/engine.py")
+    _load("text_generation_server.prompt_cache", "prompt_cache.py")
+    models = _pkg("text_generation_server.models", os.path.join(REF, "models"))
+    _load("text_generation_server.models.types", "models/types.py")
+    model_mod = _load("text_generation_server.models.model", "models/model.py")
+    models.Model = model_mod.Model
+    hub = types.ModuleType("text_generation_server.utils.hub")
+    hub.get_model_path = lambda *a, **k: None
+    sys.modules["text_generation_server.utils.hub"] = hub
+    import transformers
+    import transformers.generation.logits_process as tlp
+    if not hasattr(transformers, "LogitsWarper"):
+        transformers.LogitsWarper = transformers.LogitsProcessor
+    if not hasattr(tlp, "LogitsWarper"):
+        tlp.LogitsWarper = tlp.LogitsProcessor
+    for name, rel in (("dist", "utils/dist.py"), ("token_types", "utils/token_types.py"), ("logits_process", "utils/logits_process.py"),
+                      ("tokens", "utils/tokens.py"), ("layers", "utils/layers.py")):
+        if f"text_generation_server.utils.{name}" not in sys.modules:
+            _load(f"text_generation_server.utils.{name}", rel)
+    fcl = _load("text_generation_server.models.flash_causal_lm", "models/flash_causal_lm.py")
+
+    V = 64
+    tok = make_tokenizer(V)
+
+    def fake_logits(input_ids, position_ids):
+        g = (input_ids.to(torch.int64) * 7919 + position_ids.to(torch.int64) * 104729) % 1000003
+        base = torch.arange(V, dtype=torch.int64)[None, :]
+        return (((g[:, None] * (base + 3)) % 97).float() / 9.7 - 5.0).to(torch.float16)
+
+    class FakeModel:
+        def forward(self, input_ids, position_ids, cu_seqlens, cu_seqlens_q, max_s, inputs_embeds, past_key_values, prealloc):
+            T = input_ids.shape[0]
+            if past_key_values is None:
+                n = T if prealloc is None else prealloc
+                present = torch.zeros(1, n, 2, 1, 1, dtype=torch.float16)
+            else:
+                present = past_key_values
+            return fake_logits(input_ids, position_ids), present
+
+    lm = object.__new__(fcl.FlashCausalLM)
+    lm.model = FakeModel()
+    lm.present_pad = None
+    lm.device = torch.device("cpu")
+    lm.tokenizer = tok
+
+    def req(i, text, n_in, n_out, truncate=False):
+        return my_pb.Request(id=i, inputs=text, input_length=n_in, truncate=truncate, max_output_length=n_out,
+                             parameters=my_pb.NextTokenChooserParameters(temperature=0.0, top_p=1.0, min_new_tokens=2))
+
+    out = {}
+
+    def snap(tag, b, toks=None):
+        out[f"{tag}_input_ids"] = b.input_ids.numpy().copy()
+        out[f"{tag}_position_ids"] = b.position_ids.numpy().copy()
+        out[f"{tag}_cu_seqlens"] = b.cu_seqlens.numpy().copy()
+        out[f"{tag}_all_input_ids"] = b.all_input_ids_tensor.numpy().copy()
+        out[f"{tag}_input_lengths"] = np.array(b.input_lengths)
+        out[f"{tag}_total_lengths"] = np.array(list(b.total_lengths))
+        out[f"{tag}_max_seqlen"] = np.array(b.max_seqlen)
+        out[f"{tag}_request_ids"] = np.array([r.id for r in b.requests])
+        out[f"{tag}_current_tokens"] = np.array(b.next_token_chooser.current_tokens)
+        if toks is not None:
+            out[f"{tag}_tokens"] = np.array([[t.request_id, t.token_id] for t in toks])
+
+    msg_a = my_pb.Batch(id=0, requests=[req(0, "test <tok5> <tok9>", 3, 6), req(1, "test " * 50, 5, 6, truncate=True), req(2, "<tok7>", 1, 6)])
+    msg_b = my_pb.Batch(id=1, requests=[req(3, "<tok11> test", 2, 4)])
+    A, errs = fcl.FlashCausalLMBatch.from_pb(msg_a, tok, torch.float16, torch.device("cpu"), None, None, True)
+    snap("a0", A)
+    toks = lm.generate_token(A, first=True)[0]
+    snap("a1", A, toks)
+    for s in range(2):
+        toks = lm.generate_token(A)[0]
+        snap(f"a{2 + s}", A, toks)
+    Bb, _ = fcl.FlashCausalLMBatch.from_pb(msg_b, tok, torch.float16, torch.device("cpu"), None, None, True)
+    toks = lm.generate_token(Bb, first=True, for_concat=True)[0]
+    snap("b1", Bb, toks)
+    C = fcl.FlashCausalLMBatch.concatenate([A, Bb])
+    snap("c0", C)
+    toks = lm.generate_token(C)[0]
+    snap("c1", C, toks)
+    C = fcl.FlashCausalLMBatch.prune(C, [1])
+    snap("p0", C)
+    toks = lm.generate_token(C)[0]
+    snap("p1", C, toks)
+    out["msg_a"] = np.frombuffer(msg_a.SerializeToString(), dtype=np.uint8)
+    out["msg_b"] = np.frombuffer(msg_b.SerializeToString(), dtype=np.uint8)
+    np.savez(os.path.join(HERE, "batch_bookkeeping.npz"), **out)
+    print("batch_bookkeeping.npz", len(out))
+
+
+if __name__ == "__main__" and "--batch-only" in sys.argv:
+    gold_batch(install_stubs() if "text_generation_server" not in sys.modules else sys.modules["text_generation_server.pb"].generate_pb2)

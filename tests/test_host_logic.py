@@ -207,3 +207,86 @@ def test_world_size_2_sharded_mlp_and_embedding_over_gloo(tmp_path, quant):
     ref = full.down(oll.silu_mul(full.gate_up(x), cfg.intermediate_size)).float()
     assert (part - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 1e-3   # fp16 partial sums vs one fp32 accumulation
     assert torch.equal(e, sd["model.embed_tokens.weight"][[0, 255, 256, 511]].float())
+
+
+# ---------------------------------------------------------------------------------------------- reference bookkeeping
+def test_batch_bookkeeping_matches_reference_flash_causal_lm(mods):
+    """tests/golden/batch_bookkeeping.npz was produced by the REFERENCE's FlashCausalLMBatch.from_pb /
+    FlashCausalLM.generate_token / concatenate / prune (CPU, stand-in model.forward).  The same session through this
+    repo's classes (same stand-in forward; the device kernels of the step replaced by their torch equivalents) must
+    leave identical ids, positions, cu_seqlens, all_input_ids_tensor, lengths, chooser counters and emitted tokens."""
+    import numpy as np
+    import types
+    from tgis_b200.models.flash_causal_lm import FlashCausalLM
+    pb, Batch, tok, Mgr = mods["pb"], mods["Batch"], mods["tok"], mods["Mgr"]
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "batch_bookkeeping.npz"))
+    V = 64
+
+    def fake_logits(input_ids, position_ids):
+        g = (input_ids.to(torch.int64) * 7919 + position_ids.to(torch.int64) * 104729) % 1000003
+        base = torch.arange(V, dtype=torch.int64)[None, :]
+        return (((g[:, None] * (base + 3)) % 97).float() / 9.7 - 5.0).to(torch.float16)
+
+    class FakeModel:
+        def forward(self, input_ids, position_ids, cu_seqlens, cu_seqlens_q, max_s, inputs_embeds, past_key_values, prealloc,
+                    lm_head_indices=None):
+            lg = fake_logits(input_ids, position_ids)
+            return (lg if lm_head_indices is None else lg[lm_head_indices]), past_key_values
+
+    class HostOnlyLM(FlashCausalLM):
+        def __init__(self):
+            self.model = FakeModel()
+            self.device = torch.device("cpu")
+            self.tokenizer = tok
+            self.engine = types.SimpleNamespace(world_size=1)
+            self.kv_cache_manager = Mgr(num_layers=1, num_heads=1, emb_dim=64, kv_heads=1, device="cpu", total_num_gpu_blocks=32)
+
+        def _can_fuse_greedy(self, batch):
+            return False
+
+        def _decode_advance(self, batch):  # torch equivalent of b200_decode_advance
+            kv = batch.past_key_values
+            pos = kv.context_lens.to(torch.int64)
+            blk = kv.block_table.to(torch.int64).gather(1, (pos // 16)[:, None])[:, 0]
+            kv.slot_mapping[:len(batch)] = blk * 16 + pos % 16
+            batch.position_ids.copy_(pos)
+            kv.context_lens += 1
+
+    lm = HostOnlyLM()
+
+    def check(tag, b, toks=None):
+        assert np.array_equal(b.input_ids.numpy(), z[f"{tag}_input_ids"]), tag
+        assert np.array_equal(b.position_ids.numpy(), z[f"{tag}_position_ids"]), tag
+        assert np.array_equal(b.cu_seqlens.numpy(), z[f"{tag}_cu_seqlens"]), tag
+        ref_all = z[f"{tag}_all_input_ids"]
+        assert np.array_equal(b.all_input_ids_tensor.numpy()[:, :ref_all.shape[1]], ref_all), tag
+        assert list(b.input_lengths) == z[f"{tag}_input_lengths"].tolist(), tag
+        assert list(b.total_lengths) == z[f"{tag}_total_lengths"].tolist(), tag
+        assert b.max_seqlen == int(z[f"{tag}_max_seqlen"]), tag
+        assert [r.id for r in b.requests] == z[f"{tag}_request_ids"].tolist(), tag
+        assert list(b.next_token_chooser.current_tokens) == z[f"{tag}_current_tokens"].tolist(), tag
+        if toks is not None:
+            assert [[t.request_id, t.token_id] for t in toks] == z[f"{tag}_tokens"].tolist(), tag
+
+    msg_a = pb.Batch.FromString(z["msg_a"].tobytes())
+    msg_b = pb.Batch.FromString(z["msg_b"].tobytes())
+    A, errs = Batch.from_pb(msg_a, tok, torch.float16, torch.device("cpu"), None, None, True)
+    check("a0", A)
+    toks = lm.generate_token(A, first=True)[0]
+    check("a1", A, toks)
+    for s in range(2):
+        toks = lm.generate_token(A)[0]
+        check(f"a{2 + s}", A, toks)
+    Bb, _ = Batch.from_pb(msg_b, tok, torch.float16, torch.device("cpu"), None, None, True)
+    toks = lm.generate_token(Bb, first=True, for_concat=True)[0]
+    check("b1", Bb, toks)
+    C = Batch.concatenate([A, Bb])
+    check("c0", C)
+    toks = lm.generate_token(C)[0]
+    check("c1", C, toks)
+    C = Batch.prune(C, [1])
+    check("p0", C)
+    toks = lm.generate_token(C)[0]
+    check("p1", C, toks)
+    # the paged state agrees with the bookkeeping: context = tokens in cache, one slot per sequence for the next step
+    assert C.past_key_values.context_lens.tolist() == [L - 1 for L in C.input_lengths]

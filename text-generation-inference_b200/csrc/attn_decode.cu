@@ -43,6 +43,8 @@ attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, c
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunk = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int L = context_lens[b];
   const int tok0 = chunk * kChunkTokens;
@@ -227,6 +229,8 @@ template <int D>
 __global__ void attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                                            const int32_t* __restrict__ context_lens, __half* __restrict__ out,
                                            int64_t out_token_stride, int n_heads, int n_chunks_max) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const int L = context_lens[b];
   const int nc = (L + kChunkTokens - 1) / kChunkTokens;
@@ -266,15 +270,13 @@ static int launch_decode(const void* q, int64_t q_token_stride, const void* k_po
   float* part_ml = part_o + (int64_t)B * n_heads * n_chunks * D;
   dim3 grid(n_chunks, n_kv, B);
   b200_timing_mark(B200_TIME_ATTN_DECODE, 0, st);
-  attn_decode_paged_kernel<D><<<grid, kDecodeThreads, S::kBytes, st>>>(
-      (const __half*)q, q_token_stride, (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o,
-      part_ml, n_heads, n_kv, n_chunks, scale * 1.4426950408889634f);
+  B200_LAUNCH(attn_decode_paged_kernel<D>, grid, dim3(kDecodeThreads), (size_t)S::kBytes, st, (const __half*)q, q_token_stride,
+              (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o, part_ml, n_heads, n_kv,
+              n_chunks, scale * 1.4426950408889634f);
   b200_timing_mark(B200_TIME_ATTN_DECODE, 1, st);
-  B200_CHECK_LAUNCH();
   b200_count_launches(1);
-  attn_decode_combine_kernel<D><<<dim3(n_heads, B), D, 0, st>>>(part_o, part_ml, context_lens, (__half*)out, out_token_stride,
-                                                                n_heads, n_chunks);
-  B200_CHECK_LAUNCH();
+  B200_LAUNCH(attn_decode_combine_kernel<D>, dim3(n_heads, B), dim3(D), 0, st, (const float*)part_o, (const float*)part_ml, context_lens,
+              (__half*)out, out_token_stride, n_heads, n_chunks);
   b200_count_launches(1);
   return B200_OK;
 }

@@ -40,6 +40,8 @@ attn_prefill_varlen_kernel(const __half* __restrict__ q, int64_t q_stride, const
   unsigned char* sK = smem + kTileBytes;       // 2 buffers
   unsigned char* sV = sK + 2 * kTileBytes;     // 2 buffers
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z, head = blockIdx.y;
   const int seq0 = cu_seqlens[b], L = cu_seqlens[b + 1] - seq0;
   const int q0 = blockIdx.x * kBM;
@@ -188,9 +190,8 @@ static int launch_prefill(const void* q, int64_t qs, const void* k, int64_t ks, 
     configured = true;
   }
   dim3 grid((max_s + kBM - 1) / kBM, n_heads, B);
-  attn_prefill_varlen_kernel<D><<<grid, 128, kSmem, st>>>((const __half*)q, qs, (const __half*)k, ks, (const __half*)v, vs, cu,
-                                                          (__half*)out, os, n_heads, n_kv, scale * 1.4426950408889634f, causal);
-  B200_CHECK_LAUNCH();
+  B200_LAUNCH(attn_prefill_varlen_kernel<D>, grid, dim3(128), (size_t)kSmem, st, (const __half*)q, qs, (const __half*)k, ks, (const __half*)v,
+              vs, cu, (__half*)out, os, n_heads, n_kv, scale * 1.4426950408889634f, causal);
   b200_count_launches(1);
   return B200_OK;
 }

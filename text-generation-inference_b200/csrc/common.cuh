@@ -20,6 +20,13 @@
   } while (0)
 
 void b200_set_last_error(const char* msg);
+
+// launch through b200_launch (PDL attribute) and turn a launch error into a status code
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                        \
+    cudaError_t _e = b200_launch(kernel, grid, block, smem, stream, __VA_ARGS__);             \
+    if (_e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(_e)); return B200_ERR_CUDA; } \
+  } while (0)
 void b200_count_launches(int n);  // kernels of this library enqueued so far (bench.py "gpu_launches")
 // event pair around one launch of kernel family `which` when a timing handle is attached (runtime.cu)
 #define B200_TIME_ATTN_DECODE 1
@@ -27,7 +34,33 @@ void b200_count_launches(int n);  // kernels of this library enqueued so far (be
 #define B200_TIME_GEMM_F16 3
 void b200_timing_mark(int which, int is_stop, cudaStream_t st);
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may start while
+// the previous kernel of the stream drains.  Device side, a kernel calls pdl_launch_dependents() first thing (lets the
+// next kernel's prologue start once all of this grid's CTAs are running) and pdl_wait() before it touches anything the
+// previous kernel produced or writes anything the previous kernel may still read.  Only immutable data (weights) may be
+// read ahead of pdl_wait().  B200_PDL=0 in the environment turns the launch attribute off.
+bool b200_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t b200_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = b200_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 namespace b200 {
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 constexpr int kPageTokens = 16;  // paged KV block size (reference: models/paged_causal_lm.py:308)
 

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_residual_kernel(const __half
                                                                       const __half* __restrict__ gamma,
                                                                       __half* __restrict__ normed, __half* __restrict__ res_out,
                                                                       int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of the summed row
   __shared__ float red[32];
@@ -100,6 +102,8 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ qkv, const __half* __r
                                      const __half* __restrict__ sin_t, const int64_t* __restrict__ position_ids,
                                      const int64_t* __restrict__ slot_mapping, __half* __restrict__ k_pool,
                                      __half* __restrict__ v_pool, int n_heads, int n_kv, int rot_half) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const int head = blockIdx.y;  // [0,h): q, [h,h+kv): k, [h+kv, h+2kv): v
   const int j = threadIdx.x;    // pair index 0..d/2-1
@@ -136,6 +140,8 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ qkv, const __half* __r
 // out[t, i] = fp16( fp16(silu(g)) * u ),  gate_up [T, 2, I]
 // ------------------------------------------------------------------------------------------------
 __global__ void silu_mul_kernel(const __half* __restrict__ gate_up, __half* __restrict__ out, int64_t I, int64_t total8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total8; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t per_row = I / 8;
     const int64_t t = idx / per_row;
@@ -162,6 +168,8 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gate_up, __half* __re
 // ------------------------------------------------------------------------------------------------
 __global__ void embedding_kernel(const __half* __restrict__ table, const int64_t* __restrict__ ids, __half* __restrict__ out,
                                  int H, int64_t vocab_start, int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const int64_t id = ids[t] - vocab_start;
   const bool ok = id >= 0 && id < rows;
@@ -176,6 +184,8 @@ __global__ void embedding_kernel(const __half* __restrict__ table, const int64_t
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) argmax_kernel(const __half* __restrict__ logits, int64_t* __restrict__ out, int64_t V,
                                                        int64_t ld, const int64_t* __restrict__ banned) {
+  pdl_launch_dependents();
+  pdl_wait();
   const __half* row = logits + (size_t)blockIdx.x * ld;
   // banned[row] >= 0: that token's score counts as -inf (min_new_tokens EOS mask, utils/tokens.py:244-246)
   const int64_t ban = banned ? banned[blockIdx.x] : -1;
@@ -226,9 +236,8 @@ extern "C" int b200_rmsnorm_residual(const void* h, const void* residual, const 
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)H * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(rmsnorm_residual_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  rmsnorm_residual_kernel<256><<<(unsigned)T, 256, smem, st>>>((const __half*)h, (const __half*)residual, (const __half*)gamma,
-                                                               (__half*)normed_out, (__half*)residual_out, (int)H, eps);
-  B200_CHECK_LAUNCH();
+  B200_LAUNCH(rmsnorm_residual_kernel<256>, dim3((unsigned)T), dim3(256), smem, st, (const __half*)h, (const __half*)residual,
+              (const __half*)gamma, (__half*)normed_out, (__half*)residual_out, (int)H, eps);
   b200_count_launches(1);
   return B200_OK;
 }
@@ -240,16 +249,15 @@ extern "C" int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)T, n_heads + 2 * n_kv_heads);
   if (head_dim == 128) {
-    rope_kv_write_kernel<128><<<grid, 64, 0, st>>>((__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids, slot_mapping,
-                                                   (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 64);
+    B200_LAUNCH(rope_kv_write_kernel<128>, grid, dim3(64), 0, st, (__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids,
+                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 64);
   } else if (head_dim == 64) {
-    rope_kv_write_kernel<64><<<grid, 32, 0, st>>>((__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids, slot_mapping,
-                                                  (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 32);
+    B200_LAUNCH(rope_kv_write_kernel<64>, grid, dim3(32), 0, st, (__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids,
+                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 32);
   } else {
     b200_set_last_error("rope_kv_write_paged: head_dim must be 64 or 128");
     return B200_ERR_UNSUPPORTED;
   }
-  B200_CHECK_LAUNCH();
   b200_count_launches(1);
   return B200_OK;
 }
@@ -260,8 +268,7 @@ extern "C" int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t 
   const int64_t total8 = T * I / 8;
   int64_t blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  silu_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_up, (__half*)out, I, total8);
-  B200_CHECK_LAUNCH();
+  B200_LAUNCH(silu_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)gate_up, (__half*)out, I, total8);
   b200_count_launches(1);
   return B200_OK;
 }
@@ -270,8 +277,8 @@ extern "C" int b200_embedding(const void* table, const int64_t* ids, void* out, 
                               int64_t vocab_rows, void* stream) {
   if (T == 0) return B200_OK;
   if (H % 8 != 0) { b200_set_last_error("embedding: H % 8 != 0"); return B200_ERR_ARG; }
-  embedding_kernel<<<(unsigned)T, 128, 0, (cudaStream_t)stream>>>((const __half*)table, ids, (__half*)out, (int)H, vocab_start, vocab_rows);
-  B200_CHECK_LAUNCH();
+  B200_LAUNCH(embedding_kernel, dim3((unsigned)T), dim3(128), 0, (cudaStream_t)stream, (const __half*)table, ids, (__half*)out, (int)H,
+              vocab_start, vocab_rows);
   b200_count_launches(1);
   return B200_OK;
 }
@@ -280,8 +287,7 @@ extern "C" int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int6
                            void* stream) {
   if (B == 0) return B200_OK;
   if (ld % 8 != 0) { b200_set_last_error("argmax: row stride must be a multiple of 8 halves"); return B200_ERR_ARG; }
-  argmax_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, out_ids, V, ld, banned_ids);
-  B200_CHECK_LAUNCH();
+  B200_LAUNCH(argmax_kernel, dim3((unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const __half*)logits, out_ids, V, ld, banned_ids);
   b200_count_launches(1);
   return B200_OK;
 }

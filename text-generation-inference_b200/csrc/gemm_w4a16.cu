@@ -109,6 +109,7 @@ struct W4Params {
   int groupsize;      // > 0
   int group_rows;     // scale/zero rows per k-block = max(1, 128 / groupsize)
   unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
+  int debug_flags;            // debug timing experiments (results invalid): 1 = skip dequant math, 2 = skip tcgen05.st
 };
 
 template <int TN>
@@ -131,6 +132,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
   __shared__ int s_is_last[2];
 
+  pdl_launch_dependents();
   const int warp = warp_id(), lane = lane_id();
   const int t0 = blockIdx.y * TN;
   const int u0 = blockIdx.x * p.units_per_cta;
@@ -201,6 +203,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (elect_one()) {
       const uint64_t pol_x = policy_evict_last();
       int kb = kb0;
+      pdl_wait();  // x is the previous kernel's output; the weight ring (warp 0) is already streaming
       for (int i = 0; i < n_units; ++i) {
         const int s = i % C::kXStages;
         mbar_wait(&empty_x[s], ((i / C::kXStages) & 1) ^ 1);
@@ -294,15 +297,25 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           const __half2 z1024 = __half2half2(__ushort_as_half((unsigned short)(0x6400 + zp)));       // 1024 + zp, exact
           const __half2 z64 = __half2half2(__ushort_as_half((unsigned short)(0xD400 + (zp << 4))));  // -(64 + zp), exact
 #pragma unroll
-          for (int r = 0; r < 4; ++r) dequant_word(w[sub * 4 + r], z1024, z64, sc2, &v[(sub * 4 + r) * 4]);
+          for (int r = 0; r < 4; ++r) {
+            if (p.debug_flags & 1) {
+              v[(sub * 4 + r) * 4] = v[(sub * 4 + r) * 4 + 1] = v[(sub * 4 + r) * 4 + 2] = v[(sub * 4 + r) * 4 + 3] = w[sub * 4 + r] & 0x03ff03ffu;
+            } else {
+              dequant_word(w[sub * 4 + r], z1024, z64, sc2, &v[(sub * 4 + r) * 4]);
+            }
+          }
         }
         if (i == 8 || i == 10) W4_TRACE(40 + (i - 8) * 4);  // dequant done
         mbar_wait(&a_empty[as], ((i / kW4AStages) & 1) ^ 1);
         if (i == 8 || i == 10) W4_TRACE(41 + (i - 8) * 4);  // A stage free
         tcgen05_fence_after();
         const uint32_t ta = tmem_a + lane_base + as * kW4AColsPerStage + half * 32;
-        tmem_st_32x32b_x16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
-        tmem_st_32x32b_x16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
+        if (!(p.debug_flags & 2)) {
+          tmem_st_32x32b_x16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
+          tmem_st_32x32b_x16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
+        } else if (v[3] == 0x12345u) {
+          tmem_st_32x32b_x16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));  // keeps v alive
+        }
         trace_load = (i == 8) ? 52 : (i == 10) ? 53 : 0;
         if (i + 2 < n_units) load_unit();  // overlaps the TMEM store latency
         if (i == 8 || i == 10) W4_TRACE(42 + (i - 8) * 4);  // next unit's words in registers
@@ -315,6 +328,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
         if (seg_last) {
           // -------------------------------------------------------------- epilogue of this tile segment (this group)
+          pdl_wait();  // outputs / bias / stream-K workspace belong to the stream order
           const int n = tile * kW4TileM + m;
           const bool n_ok = n < p.N;
           // contributors of this tile: CTAs whose unit range intersects [tile*nkb, (tile+1)*nkb)
@@ -447,6 +461,7 @@ __global__ void gptq_repack_kernel(uint32_t* __restrict__ qweight, int64_t n_wor
 }
 
 static unsigned long long* g_w4_trace = nullptr;
+static int g_w4_debug_flags = 0;
 
 static int num_sms() {
   static int n = 0;
@@ -488,7 +503,7 @@ using namespace b200;
 
 // debug: device buffer of [n_ctas][64] uint64 receiving per-CTA phase timestamps of the next int4 GEMM launches
 extern "C" void b200_debug_w4_trace(void* device_buffer) { g_w4_trace = (unsigned long long*)device_buffer; }
-extern "C" void b200_debug_w4_flags(int) {}
+extern "C" void b200_debug_w4_flags(int flags) { g_w4_debug_flags = flags; }
 
 extern "C" int b200_gptq_repack(void* qweight, int64_t K, int64_t N, int inverse, void* stream) {
   if (K % 8 != 0) { b200_set_last_error("gptq_repack: K % 8 != 0"); return B200_ERR_ARG; }
@@ -534,11 +549,11 @@ static int launch_gemm_w4(const CUtensorMap* mq, const CUtensorMap* mx, const CU
   p.groupsize = groupsize;
   p.group_rows = groupsize >= kW4BlockK ? 1 : kW4BlockK / groupsize;
   p.trace = g_w4_trace;
+  p.debug_flags = g_w4_debug_flags;
   dim3 grid(pl.n_ctas, pl.n_tiles_t, 1);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 0, st);
-  gemm_w4a16_kernel<TN><<<grid, kW4Threads, C::kSmemBytes, st>>>(*mq, *mx, *ms, *mz, p);
+  B200_LAUNCH(gemm_w4a16_kernel<TN>, grid, dim3(kW4Threads), (size_t)C::kSmemBytes, st, *mq, *mx, *ms, *mz, p);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 1, st);
-  B200_CHECK_LAUNCH();
   b200_count_launches(1);
   return B200_OK;
 }

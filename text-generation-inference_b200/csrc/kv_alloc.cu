@@ -67,6 +67,8 @@ namespace b200 {
 __global__ void decode_advance_kernel(const int32_t* __restrict__ block_table, int64_t bt_stride, int32_t* __restrict__ context_lens,
                                       int64_t* __restrict__ position_ids, int64_t* __restrict__ slot_mapping,
                                       const int64_t* __restrict__ next_ids, int64_t* __restrict__ input_ids, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int pos = context_lens[b];
@@ -88,9 +90,8 @@ extern "C" int b200_decode_advance(const int32_t* block_table, int64_t block_tab
                                    int64_t* position_ids, int64_t* slot_mapping, const int64_t* next_ids, int64_t* input_ids,
                                    int B, void* stream) {
   if (B == 0) return B200_OK;
-  b200::decode_advance_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(block_table, block_table_stride, context_lens,
-                                                                                 position_ids, slot_mapping, next_ids, input_ids, B);
-  B200_CHECK_LAUNCH();
+  B200_LAUNCH(b200::decode_advance_kernel, dim3((B + 127) / 128), dim3(128), 0, (cudaStream_t)stream, block_table, block_table_stride,
+              context_lens, position_ids, slot_mapping, next_ids, input_ids, B);
   b200_count_launches(1);
   return B200_OK;
 }

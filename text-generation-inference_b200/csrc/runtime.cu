@@ -17,6 +17,15 @@ static std::atomic<long long> g_launches{0};
 void b200_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" int64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+bool b200_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_PDL");
+    v = (e && (e[0] == '0' || e[0] == 'f' || e[0] == 'F')) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" const char* b200_last_error(void) { return g_last_error.c_str(); }
 // debug aid: pending CUDA runtime error of this library's runtime instance (does not clear it)
 extern "C" const char* b200_cuda_peek_error(void) { return cudaGetErrorString(cudaPeekAtLastError()); }

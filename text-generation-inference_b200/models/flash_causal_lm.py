@@ -253,10 +253,7 @@ class FlashCausalLM(Model):
             if self._can_fuse_greedy(batch):
                 generated, errs, forward_time_ns = self._decode_fused_greedy(batch)
             else:
-                # device bookkeeping: position = tokens cached, slot from the block table, context += 1
-                _lib.check(_lib.load().b200_decode_advance(
-                    kv.block_table.data_ptr(), kv.block_table.stride(0), kv.context_lens.data_ptr(), batch.position_ids.data_ptr(),
-                    kv.slot_mapping.data_ptr(), None, None, B, torch.cuda.current_stream().cuda_stream), "decode_advance")
+                self._decode_advance(batch)
                 start_time = time.time_ns()
                 out, _ = self.model.forward(batch.input_ids, batch.position_ids, batch.cu_seqlens, batch.cu_seqlens_q,
                                             batch.max_seqlen, None, kv, None, None)
@@ -266,6 +263,14 @@ class FlashCausalLM(Model):
         batch.cu_seqlens.add_(batch.cu_seqlens_q)
         batch.max_seqlen += 1
         return generated, input_infos, errs, forward_time_ns
+
+    def _decode_advance(self, batch) -> None:
+        """device bookkeeping at the start of a decode step: position = tokens cached, slot from the block table,
+        context += 1 (csrc/kv_alloc.cu)"""
+        kv = batch.past_key_values
+        _lib.check(_lib.load().b200_decode_advance(
+            kv.block_table.data_ptr(), kv.block_table.stride(0), kv.context_lens.data_ptr(), batch.position_ids.data_ptr(),
+            kv.slot_mapping.data_ptr(), None, None, len(batch), torch.cuda.current_stream().cuda_stream), "decode_advance")
 
     # --------------------------------------------------------------------------------------------- fused greedy decode
     def _can_fuse_greedy(self, batch) -> bool:

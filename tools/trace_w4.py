@@ -10,7 +10,7 @@ from tgis_b200 import _lib, ops  # noqa: E402
 
 dev = "cuda:0"
 lib = _lib.load()
-for flags, T, N, K in [(0, 64, 22016, 4096)]:
+for flags, T, N, K in [(0, 64, 22016, 4096), (1, 64, 22016, 4096), (2, 64, 22016, 4096), (3, 64, 22016, 4096)]:
     lib.b200_debug_w4_flags(flags)
     x = torch.randn(T, K, device=dev).half()
     qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (K // 8, N), device=dev, dtype=torch.int32)
