@@ -361,8 +361,20 @@ def run_gpu(args, workload):
                                         "sample": f"failed: {type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # NCCL kernels live inside the captured CUDA graphs: tearing the communicator down while they exist can hang, so
+        # rendezvous on the host-side store instead of an NCCL barrier, then leave without destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            store.add("bench_done", 1)
+            t_end = time.time() + 30
+            while int(store.add("bench_done", 0)) < world and time.time() < t_end:
+                time.sleep(0.05)
+        except Exception:
+            time.sleep(1.0)
+        os._exit(0)
     return 0
 
 

@@ -16,7 +16,8 @@
 
 namespace b200 {
 
-constexpr int kChunkTokens = 512;
+constexpr int kMaxChunkTokens = 512;  // <= 32 pages: the producer warp holds one block id per lane
+constexpr int kMinChunkTokens = 128;
 constexpr int kPagesPerStage = 4;
 constexpr int kConsumerWarps = 4;
 constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 2)
 attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, const __half* __restrict__ k_pool,
                          const __half* __restrict__ v_pool, const int32_t* __restrict__ block_table, int64_t bt_stride,
                          const int32_t* __restrict__ context_lens, float* __restrict__ part_o, float* __restrict__ part_ml,
-                         int n_heads, int n_kv, int n_chunks_max, float scale_log2) {
+                         int n_heads, int n_kv, int n_chunks_max, int chunk_tokens, float scale_log2) {
   using S = DecodeSmem<D>;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stages = smem;
@@ -47,9 +48,9 @@ attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, c
   pdl_wait();
   const int chunk = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int L = context_lens[b];
-  const int tok0 = chunk * kChunkTokens;
+  const int tok0 = chunk * chunk_tokens;
   if (tok0 >= L) return;
-  const int n_tok = min(kChunkTokens, L - tok0);
+  const int n_tok = min(chunk_tokens, L - tok0);
   const int n_pages = (n_tok + kPageTokens - 1) / kPageTokens;
   const int n_iters = (n_pages + kPagesPerStage - 1) / kPagesPerStage;
   const int G = n_heads / n_kv;
@@ -228,12 +229,12 @@ attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, c
 template <int D>
 __global__ void attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                                            const int32_t* __restrict__ context_lens, __half* __restrict__ out,
-                                           int64_t out_token_stride, int n_heads, int n_chunks_max) {
+                                           int64_t out_token_stride, int n_heads, int n_chunks_max, int chunk_tokens) {
   pdl_launch_dependents();
   pdl_wait();
   const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const int L = context_lens[b];
-  const int nc = (L + kChunkTokens - 1) / kChunkTokens;
+  const int nc = (L + chunk_tokens - 1) / chunk_tokens;
   const int64_t base = ((int64_t)b * n_heads + head) * n_chunks_max;
   float M = kNegBig;
   for (int c = 0; c < nc; ++c) M = fmaxf(M, part_ml[(base + c) * 2]);
@@ -251,14 +252,14 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ part_o, con
 using namespace b200;
 
 extern "C" int64_t b200_attn_decode_workspace_bytes(int B, int n_heads, int head_dim, int max_context_len) {
-  const int64_t nc = (max_context_len + kChunkTokens - 1) / kChunkTokens;
+  const int64_t nc = (max_context_len + kMinChunkTokens - 1) / kMinChunkTokens;  // sized for the smallest chunk
   return (int64_t)B * n_heads * (nc > 0 ? nc : 1) * (head_dim + 2) * 4;
 }
 
 template <int D>
 static int launch_decode(const void* q, int64_t q_token_stride, const void* k_pool, const void* v_pool, const int32_t* block_table,
                          int64_t bt_stride, const int32_t* context_lens, void* out, int64_t out_token_stride, void* workspace,
-                         int B, int n_heads, int n_kv, int n_chunks, float scale, cudaStream_t st) {
+                         int B, int n_heads, int n_kv, int n_chunks, int chunk_tokens, float scale, cudaStream_t st) {
   using S = DecodeSmem<D>;
   static bool configured = false;
   if (!configured) {
@@ -272,11 +273,11 @@ static int launch_decode(const void* q, int64_t q_token_stride, const void* k_po
   b200_timing_mark(B200_TIME_ATTN_DECODE, 0, st);
   B200_LAUNCH(attn_decode_paged_kernel<D>, grid, dim3(kDecodeThreads), (size_t)S::kBytes, st, (const __half*)q, q_token_stride,
               (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o, part_ml, n_heads, n_kv,
-              n_chunks, scale * 1.4426950408889634f);
+              n_chunks, chunk_tokens, scale * 1.4426950408889634f);
   b200_timing_mark(B200_TIME_ATTN_DECODE, 1, st);
   b200_count_launches(1);
   B200_LAUNCH(attn_decode_combine_kernel<D>, dim3(n_heads, B), dim3(D), 0, st, (const float*)part_o, (const float*)part_ml, context_lens,
-              (__half*)out, out_token_stride, n_heads, n_chunks);
+              (__half*)out, out_token_stride, n_heads, n_chunks, chunk_tokens);
   b200_count_launches(1);
   return B200_OK;
 }
@@ -296,15 +297,20 @@ extern "C" int b200_attn_decode_paged(const void* q, int64_t q_token_stride, con
     return B200_ERR_ARG;
   }
   if ((q_token_stride & 1) || ((uintptr_t)q & 3)) { b200_set_last_error("attn_decode_paged: q must be 4-byte aligned"); return B200_ERR_ARG; }
-  int n_chunks = (max_context_len + kChunkTokens - 1) / kChunkTokens;
+  // split-KV granularity: the largest chunk that still gives every SM several CTAs (2 resident CTAs x 148 SMs)
+  int chunk_tokens = kMaxChunkTokens;
+  while (chunk_tokens > kMinChunkTokens &&
+         (int64_t)B * n_kv_heads * ((max_context_len + chunk_tokens - 1) / chunk_tokens) < 4 * 296)
+    chunk_tokens >>= 1;
+  int n_chunks = (max_context_len + chunk_tokens - 1) / chunk_tokens;
   if (n_chunks < 1) n_chunks = 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (head_dim == 128)
     return launch_decode<128>(q, q_token_stride, k_pool, v_pool, block_table, block_table_stride, context_lens, out,
-                              out_token_stride, workspace, B, n_heads, n_kv_heads, n_chunks, softmax_scale, st);
+                              out_token_stride, workspace, B, n_heads, n_kv_heads, n_chunks, chunk_tokens, softmax_scale, st);
   if (head_dim == 64)
     return launch_decode<64>(q, q_token_stride, k_pool, v_pool, block_table, block_table_stride, context_lens, out,
-                             out_token_stride, workspace, B, n_heads, n_kv_heads, n_chunks, softmax_scale, st);
+                             out_token_stride, workspace, B, n_heads, n_kv_heads, n_chunks, chunk_tokens, softmax_scale, st);
   b200_set_last_error("attn_decode_paged: head_dim must be 64 or 128");
   return B200_ERR_UNSUPPORTED;
 }
