@@ -29,7 +29,7 @@ extern "C" {
 int b200_abi_version(void);
 const char* b200_last_error(void);
 const char* b200_cuda_peek_error(void); /* debug: pending CUDA runtime error string, not cleared */
-void b200_debug_w4_flags(int flags); /* debug: timing experiments (results invalid): 1 no scale/zero TMA, 2 no activation TMA, 4 one MMA per unit */
+void b200_debug_w4_flags(int flags); /* debug timing experiments (results invalid): 1 no x loads, 2 no MMAs, 4 no weight loads, 8 no dequant math */
 void b200_debug_w4_trace(void* device_buffer); /* debug: [n_ctas][64] u64 phase timestamps of int4 GEMM launches; NULL = off */
 /* number of kernels this library has enqueued in this process (bench.py reports the delta as "gpu_launches") */
 int64_t b200_launch_count(void);
@@ -106,15 +106,21 @@ int64_t b200_gemm_workspace_bytes_max(int64_t N, int64_t K); /* max over all T: 
 int b200_gemm_f16(const void* x, const void* w, const void* bias, void* y, int64_t T, int64_t N, int64_t K, void* workspace,
                   void* stream);
 
-/* one-time in-place nibble re-order of GPTQ qweight int32 [K/8, N]; replaces exllamav2_kernels.make_q_matrix
- * (utils/gptq/exllamav2.py:23-62).  inverse != 0 restores the checkpoint layout. */
-int b200_gptq_repack(void* qweight, int64_t K, int64_t N, int inverse, void* stream);
+/* one-time conversion of the GPTQ checkpoint tensors of one linear into the kernel's streaming layout ("unit records":
+ * one contiguous 8 KB + meta block per (128-feature tile, 128-wide k-block)); replaces
+ * exllamav2_kernels.make_q_matrix (utils/gptq/exllamav2.py:23-62), `packed` plays the role of its q_handle.
+ * qweight int32 [K/8, N], qzeros int32 [ceil(K/g), N/8], scales fp16 [ceil(K/g), N] in checkpoint layout (read only; the
+ * caller may free them afterwards).  groupsize: 32, 64, a multiple of 128, or <= 0 for one group; groups are
+ * k // groupsize (trivial g_idx; act-order is rejected by the host wrapper).  K % 32 == 0, N % 32 == 0
+ * (exllamav2.py:118-119).  packed: b200_gptq_packed_bytes(K, N, groupsize) bytes, 16-byte aligned. */
+int64_t b200_gptq_packed_bytes(int64_t K, int64_t N, int groupsize);
+int b200_gptq_pack(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
+                   int groupsize, void* stream);
 
-/* y[T,N] = x[T,K] . dequant(qweight, qzeros, scales) (+ bias);  replaces exllamav2_kernels.gemm_half_q_half
- * (utils/gptq/exllamav2.py:14-20).  qzeros int32 [K/g, N/8], scales fp16 [K/g, N] in checkpoint layout;
- * groups are k // groupsize (trivial g_idx; act-order is rejected by the host wrapper). */
-int b200_gemm_w4a16(const void* x, const void* qweight_repacked, const void* qzeros, const void* scales, const void* bias,
-                    void* y, int64_t T, int64_t N, int64_t K, int groupsize, void* workspace, void* stream);
+/* y[T,N] = x[T,K] . dequant(packed) (+ bias);  replaces exllamav2_kernels.gemm_half_q_half
+ * (utils/gptq/exllamav2.py:14-20) for every T (no dequant-to-scratch branch, cf. :87). */
+int b200_gemm_w4a16(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
+                    int groupsize, void* workspace, void* stream);
 
 /* ---- paged KV block allocator (host) + per-step bookkeeping (device) -------------------------------------
  * replaces fms-extras PagedKVCacheManager block bookkeeping (models/paged_causal_lm.py:338-353,
@@ -136,9 +142,9 @@ int b200_decode_advance(const int32_t* block_table, int64_t block_table_stride, 
  * memory owned by the caller (weights: the model; scratch: the host runtime). */
 typedef struct {
   const void* weight;  /* fp16 [N, K], or NULL when GPTQ */
-  const void* qweight; /* int32 [K/8, N] after b200_gptq_repack, or NULL */
-  const void* qzeros;  /* int32 [K/g, N/8] */
-  const void* scales;  /* fp16 [K/g, N] */
+  const void* qweight; /* GPTQ: the b200_gptq_pack output for this linear, or NULL */
+  const void* qzeros;  /* unused (folded into the packed records); kept for layout stability */
+  const void* scales;  /* unused */
   const void* bias;    /* fp16 [N] or NULL */
   int64_t N, K;
   int32_t groupsize;

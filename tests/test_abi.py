@@ -28,7 +28,7 @@ def _header_symbols():
 def test_header_declares_the_expected_surface():
     syms = _header_symbols()
     for s in ["b200_rmsnorm_residual", "b200_rope_kv_write_paged", "b200_attn_prefill_varlen", "b200_attn_decode_paged",
-              "b200_gptq_repack", "b200_gemm_w4a16", "b200_gemm_f16", "b200_silu_mul", "b200_argmax", "b200_embedding",
+              "b200_gptq_packed_bytes", "b200_gptq_pack", "b200_gemm_w4a16", "b200_gemm_f16", "b200_silu_mul", "b200_argmax", "b200_embedding",
               "b200_kv_alloc_create", "b200_kv_alloc_take", "b200_kv_alloc_release", "b200_llama_step"]:
         assert s in syms, s
 

@@ -64,20 +64,41 @@ def test_gemm_f16_bias(ops):
     _close(ops.gemm_f16(x.to(DEV), w.to(DEV), b.to(DEV)), ref, what="gemm_f16 bias")
 
 
-def test_gptq_repack_roundtrip(ops):
+def test_gptq_pack_layout(ops):
+    """b200_gptq_pack output == the documented unit-record layout, built here with plain indexing."""
     g = torch.Generator().manual_seed(11)
-    q = torch.randint(-2 ** 31, 2 ** 31 - 1, (64, 256), generator=g, dtype=torch.int64).to(torch.int32)
-    d = q.clone().to(DEV)
-    ops.gptq_repack(d)
-    rp = d.cpu()
-    # nibble k of the original sits at position (k & 1) * 4 + (k >> 1)
-    qu = q.to(torch.int64) & 0xFFFFFFFF
-    ru = rp.to(torch.int64) & 0xFFFFFFFF
-    for k in range(8):
-        pos = (k & 1) * 4 + (k >> 1)
-        assert torch.equal((qu >> (4 * k)) & 15, (ru >> (4 * pos)) & 15)
-    ops.gptq_repack(d, inverse=True)
-    assert torch.equal(d.cpu(), q)
+    K, N, gs = 320, 288, 64  # ragged: 3 k-blocks (last half empty), 3 feature tiles (third has 32 features) padded to 2 super-tiles, 2 meta rows
+    qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (K // 8, N), generator=g, dtype=torch.int64).to(torch.int32)
+    qz = torch.randint(-2 ** 31, 2 ** 31 - 1, (K // gs, N // 8), generator=g, dtype=torch.int64).to(torch.int32)
+    sc = torch.randn(K // gs, N, generator=g).half()
+    packed = ops.gptq_pack(qw.to(DEV), qz.to(DEV), sc.to(DEV), gs).cpu()
+    nkb, nt, gr = 3, 4, 2
+    # records are ordered (super-tile = pair of feature tiles, k-block, tile within the pair)
+    rec = (packed.view(torch.int32).to(torch.int64).view(nt // 2, nkb, 2, (8192 + gr * 512) // 4) & 0xFFFFFFFF).permute(0, 2, 1, 3)
+    rec = rec.reshape(nt, nkb, -1)
+    q = ogptq.unpack_rows_int4(qw.numpy())                 # [K, N] nibbles
+    z = ogptq.unpack_cols_int4(qz.numpy()).astype("int64") + 1  # [G, N]
+    sbits = sc.view(torch.int16).to(torch.int64) & 0xFFFF
+    for tile in range(nt):
+        for kb in range(nkb):
+            words = rec[tile, kb, :2048].view(4, 128, 4)
+            meta = rec[tile, kb, 2048:].view(gr, 128)
+            for m in (0, 1, 31, 32, 127):
+                n = tile * 128 + m
+                for c in range(4):
+                    for j in range(4):
+                        k0 = kb * 128 + c * 32 + j * 8
+                        exp = 0
+                        if n < N and k0 < K:
+                            for k in range(8):
+                                exp |= int(q[k0 + k, n]) << (4 * ((k & 1) * 4 + (k >> 1)))
+                        assert int(words[c, m, j]) == exp, (tile, kb, c, m, j)
+                for r in range(gr):
+                    k0 = kb * 128 + r * 64
+                    exp = 1 << 16
+                    if n < N and k0 < K:
+                        exp = int(sbits[k0 // gs, n]) | (int(z[k0 // gs, n]) << 16)
+                    assert int(meta[r, m]) == exp, (tile, kb, r, m)
 
 
 W4_SHAPES = [(64, 4096, 4096, 128), (1, 256, 128, 128), (7, 384, 256, 64), (16, 128, 64, 32), (33, 2560, 2048, 128),
@@ -93,9 +114,8 @@ def test_gemm_w4a16(ops, T, N, K, gs):
     qzeros = torch.randint(-2 ** 31, 2 ** 31 - 1, qzeros.shape, generator=g, dtype=torch.int64).to(torch.int32)
     x = torch.randn(T, K, generator=g).half()
     ref = ogptq.gemm_half_q_half(x, qweight, qzeros, scales, None, gs)
-    qw_d = qweight.clone().to(DEV)
-    ops.gptq_repack(qw_d)
-    got = ops.gemm_w4a16(x.to(DEV), qw_d, qzeros.to(DEV), scales.to(DEV), gs)
+    packed = ops.gptq_pack(qweight.to(DEV), qzeros.to(DEV), scales.to(DEV), gs)
+    got = ops.gemm_w4a16(x.to(DEV), packed, N, gs)
     torch.cuda.synchronize()
     _close(got, ref, what=f"gemm_w4a16 {T}x{N}x{K} g{gs}")
 
@@ -112,9 +132,8 @@ def test_gemm_w4a16_dequant_bit_exact(ops):
     x = torch.zeros(len(ks), K, dtype=torch.float16)
     for i, k in enumerate(ks):
         x[i, k] = 1.0
-    qw_d = qweight.clone().to(DEV)
-    ops.gptq_repack(qw_d)
-    got = ops.gemm_w4a16(x.to(DEV), qw_d, qzeros.to(DEV), scales.to(DEV), gs).cpu()
+    packed = ops.gptq_pack(qweight.to(DEV), qzeros.to(DEV), scales.to(DEV), gs)
+    got = ops.gemm_w4a16(x.to(DEV), packed, N, gs).cpu()
     exp = wd[ks]
     if not torch.equal(got, exp):
         bad = torch.nonzero(got != exp)

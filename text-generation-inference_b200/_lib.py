@@ -33,8 +33,9 @@ SIGNATURES = {
     "b200_gemm_workspace_bytes": (_L, [_L, _L, _L]),
     "b200_gemm_workspace_bytes_max": (_L, [_L, _L]),
     "b200_gemm_f16": (_I, [_P, _P, _P, _P, _L, _L, _L, _P, _P]),
-    "b200_gptq_repack": (_I, [_P, _L, _L, _I, _P]),
-    "b200_gemm_w4a16": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P, _P]),
+    "b200_gptq_packed_bytes": (_L, [_L, _L, _I]),
+    "b200_gptq_pack": (_I, [_P, _P, _P, _P, _L, _L, _I, _P]),
+    "b200_gemm_w4a16": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _P, _P]),
 }
 
 

@@ -6,53 +6,80 @@
 // "dequantise everything to temp_dq, then cuBLAS" branch (:87), and follows the dequant formula of record
 // utils/gptq/quant_linear.py:184-192:  W[k,n] = fp16( scales[g,n] * (q[k,n] - (qzeros[g,n] + 1)) ).
 //
-// Swap-AB like gemm_f16.cu: 128 output features = UMMA M.  Work unit = (feature tile, 128-wide k-block).
-//   warp 0       TMA, weight ring (12 deep): packed int4 tile [16 words x 128 features] (8 KB) + its scale / zero rows.
-//                Deep because only these bytes come from HBM: ~100 KB in flight per SM covers the DRAM latency.
-//   warp 2       TMA, activation ring (4 deep): [TN x 128] fp16 as two 128B-swizzled [TN x 64] sub-tiles (L2 hits)
-//   warps 3..18  dequant, two groups of 8 warps on alternate units: thread = one feature row, 64 of the 128 k per warp;
-//                LOP3 nibble-pair extraction with the 0x6400 magic bias, exact zero-point subtraction (HADD2 / HFMA2 x 1/16),
-//                one HMUL2 by the group scale -> 32 packed fp16 pairs -> tcgen05.st into a 4-deep ring of A-operand tiles in
-//                TMEM (64 columns each); the next unit's words are fetched while the stores retire
-//   warp 1       one thread issues 8 x tcgen05.mma.kind::f16 per unit (A from TMEM, B from shared memory, D fp32 in TMEM)
-//   warps 3..18  epilogue at the end of a tile segment (the group that owns its last unit): tcgen05.ld -> fp16 -> HBM
-// Decode (T <= 128) is weight-streaming / HBM-bound: the flattened (tile, k-block) unit space is cut into equal
-// contiguous ranges, one per SM (stream-K).  A tile that straddles CTAs gets its fp32 partials summed in contributor
-// order by the last CTA to finish (deterministic, unlike the reference kernel's fp16 atomicAdd across K slices).
-// `b200_gptq_repack` re-orders the 8 nibbles of every qweight word once at load time (k0 k2 k4 k6 | k1 k3 k5 k7)
-// so that one LOP3 yields a (k, k+1) half2 pair; scales / qzeros stay in the checkpoint layout.
+// Weight format.  `b200_gptq_pack` (the make_q_matrix analogue, once per linear at load time) turns the checkpoint
+// tensors into a stream of self-contained UNIT RECORDS, one per (128-feature tile, 128-wide k-block), tile-major:
+//     words  [4 chunks][128 features][4 x u32]   8 KB   chunk c = k 32c..32c+31 of the block; inside a word the 8 nibbles
+//                                                        are ordered k0 k2 k4 k6 | k1 k3 k5 k7 so one LOP3 yields a (k, k+1) pair
+//     meta   [group_rows][128 features] u32      512 B per row: fp16 scale | (zero + 1) << 16, group_rows = max(1, 128 / groupsize)
+// A CTA's work is a contiguous range of units == a contiguous byte range of HBM: one cp.async.bulk (TMA) per unit, no
+// tensor map, and the shared-memory image is exactly what the dequant threads want (LDS.128, conflict free).
 //
-// mbarrier rule used throughout: every thread that waits on a barrier waits on every phase of it, in order (a parity
-// wait that skipped a phase could be satisfied by the phase before).  Hence even ring depths (a stage always belongs
-// to the same dequant group) and the "observe only" wait on tmem_full by the group that does not own a segment.
+// Swap-AB like gemm_f16.cu: 128 output features = UMMA M, tokens = UMMA N (TN = 16..128), fp32 accumulator in TMEM.
+//   warp 0        TMA: unit records -> 16-deep (8 at TN = 128) weight ring.  Only these bytes come from HBM.
+//   warp 2        TMA: activations [TN x 128] fp16 as two 128B-swizzled sub-tiles -> 4-deep ring (L2 hits)
+//   warps 3..18   dequant: 4 teams x 4 warps; team = unit index mod 4, warp = TMEM lane quarter, thread = one feature row x
+//                 all 128 k of the unit (16 words).  Per 8 weights: 4 LOP3 + SHF (magic-number fp16: 1024 + q / 64 + q),
+//                 4 HADD2 (exact q - zero), 4 HMUL2 (x scale: bit-identical to the formula of record) -> tcgen05.st into a
+//                 ring of A-operand tiles in TMEM (64 columns each).  Teams run on their own clocks; nothing but
+//                 mbarriers couples them to the producers or the MMA warp.
+//   warp 1        one thread issues 8 x tcgen05.mma.kind::f16 per unit (A from TMEM, B from shared memory)
+//   warps 19..22  epilogue: tcgen05.ld of the finished accumulator (double buffered: the next tile's MMAs run meanwhile),
+//                 fp16 store, or fp32 partial store when the tile is shared with other CTAs
+// Decode (T <= 128) is weight-streaming / HBM-bound: the flattened (tile, k-block) unit space is cut into equal
+// contiguous ranges, one per SM (stream-K).  Tiles that straddle CTAs are finished after the main loop by ALL their
+// contributors: each sums one slice of the tile over the contributors' fp32 partials in contributor order
+// (deterministic, unlike the reference kernel's fp16 atomicAdd across K slices; a reduce-scatter, so the tail costs
+// one partial's worth of L2 reads per CTA however many CTAs share the tile).
+//
+// mbarrier rule used throughout: a thread that waits on a barrier observes every phase of it in order, or an earlier
+// observation implies the skipped phase completed (see the ring-depth static_asserts).
 #include "common.cuh"
 #include "tmap.cuh"
 
+#include <string>
+
 namespace b200 {
 
-constexpr int kW4Threads = 19 * 32;  // W-TMA warp, MMA warp, X-TMA warp, 2 groups of 8 dequant/epilogue warps
-constexpr int kW4FirstDqWarp = 3;
 constexpr int kW4TileM = 128;
 constexpr int kW4BlockK = 128;
-constexpr int kW4AStages = 4;         // TMEM A-operand ring
+constexpr int kW4WordBytes = (kW4BlockK / 8) * kW4TileM * 4;  // 8192
+constexpr int kW4MetaRowBytes = kW4TileM * 4;                 // 512
+constexpr int kW4MaxGroupRows = 4;                            // groupsize >= 32
+constexpr int kW4RecMaxBytes = kW4WordBytes + kW4MaxGroupRows * kW4MetaRowBytes;  // 10240 = shared-memory stage stride
+// Warp roles.  The SM sub-partition arbiter favours the higher warp id, so the three single-thread roles that pace the
+// pipeline (MMA issue, the two TMA producers) get the highest ids, the 16 issue-bound dequant warps sit in the middle and
+// the mostly-waiting epilogue warps get the lowest (and sleep while they wait).
+constexpr int kW4Teams = 4;
+constexpr int kW4EpWarps = 4;                                   // warps 0..3
+constexpr int kW4FirstDqWarp = kW4EpWarps;                      // warps 4..19
+constexpr int kW4MmaWarp = kW4FirstDqWarp + 4 * kW4Teams;       // 20
+constexpr int kW4WProdWarp = kW4MmaWarp + 1;                    // 21
+constexpr int kW4XProdWarp = kW4MmaWarp + 2;                    // 22
+constexpr int kW4Threads = (kW4XProdWarp + 1) * 32;             // 736
 constexpr int kW4AColsPerStage = 64;  // 128 fp16 per row = 64 x 32-bit columns
-constexpr int kW4MaxGroupRows = 4;    // groupsize >= 32
 constexpr int64_t kW4CounterBytes = 64 * 1024;
+
+constexpr int kW4R = 2;  // feature tiles per super-tile: consecutive units (super-tile, k-block, r = 0..1) share one activation tile
 
 template <int TN>
 struct GemmW4Cfg {
-  static constexpr int kQBytes = (kW4BlockK / 8) * kW4TileM * 4;        // 8192
-  static constexpr int kSBytes = kW4MaxGroupRows * kW4TileM * 2;        // 1024
-  static constexpr int kZBytes = kW4MaxGroupRows * (kW4TileM / 8) * 4;  // 256
-  static constexpr int kWStageBytes = kQBytes + kSBytes + kZBytes;      // 9472 = 74 * 128
-  static constexpr int kXSubBytes = TN * 128;                           // one [TN x 64] fp16 sub-tile
-  static constexpr int kXStageBytes = 2 * kXSubBytes;
-  static constexpr int kXStages = 4;
-  static constexpr int kWStages = TN <= 64 ? 12 : 8;
+  static constexpr int kSuRing = TN >= 128 ? 2 : 3;            // super-units whose A tiles fit in TMEM at once
+  static constexpr int kAStages = kSuRing * kW4R;              // TMEM A-operand ring (per unit)
+  static constexpr int kDBufs = TN >= 64 ? 1 : 2;              // accumulator sets (one set = kW4R tiles x TN columns)
+  static constexpr int kDCols = kDBufs * kW4R * TN;
+  static constexpr int kABase = kDCols < 64 ? 64 : kDCols;
   static constexpr int kTmemCols = 512;
-  static constexpr int kNumBars = 2 * kWStages + 2 * kXStages + 2 * kW4AStages + 2;
-  static constexpr int kSmemBytes = kXStages * kXStageBytes + kWStages * kWStageBytes + kNumBars * 8 + 16 + 1024;
-  static_assert(kWStages % 2 == 0 && kWStages >= 4, "weight ring: even depth, >= 4 (dequant warps prefetch two units ahead)");
+  static constexpr int kXSubBytes = TN * 128;                  // one [TN x 64] fp16 sub-tile
+  static constexpr int kXStageBytes = 2 * kXSubBytes;
+  static constexpr int kXStages = TN >= 128 ? 4 : 6;           // activation ring (per super-unit = kW4R units)
+  static constexpr int kWStages = TN >= 128 ? 8 : (TN == 64 ? 12 : 16);
+  static constexpr int kNumBars = 2 * kWStages + kXStages + kSuRing + 4;
+  static constexpr int kSmemBytes = kXStages * kXStageBytes + kWStages * kW4RecMaxBytes + kNumBars * 8 + 16 + 1024;
+  static_assert(kABase + kAStages * kW4AColsPerStage <= kTmemCols, "TMEM budget");
+  // a team observes every phase of the weight stages it uses only if a stage always belongs to the same team
+  static_assert(kWStages % kW4Teams == 0, "weight ring depth must be a multiple of the team count");
+  // a team at super-unit j has seen super-unit j - 2 - kSuRing complete, which implies j - 2 kSuRing did (no phase aliasing)
+  static_assert(kSuRing >= 2, "A ring depth");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -61,113 +88,158 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));  // (a & b) | c
   return r;
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ uint16_t lds_u16(uint32_t addr) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+__device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t* v) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t hadd2_u(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t hmul2_u(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_acquire_cta(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_cta_shared_inc(uint32_t* p) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// non-blocking poll (mbarrier.try_wait may suspend the thread until a time-out when the phase is still pending)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait of a warp that has nothing else to do for a long time: sleep between polls so it does not take issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 23)) { __trap(); }
+  }
+}
 
-// one repacked word (8 weights along k) -> 4 half2 (k,k+1) pairs, each fp16(scale * (q - zero))
-__device__ __forceinline__ void dequant_word(uint32_t w, __half2 z1024, __half2 z64, __half2 scale, uint32_t* out) {
-  const uint32_t kMagic = 0x64006400u;  // half2(1024, 1024)
-  const __half2 k16th = __floats2half2_rn(0.0625f, 0.0625f);
-  uint32_t q0 = lop3_and_or(w, 0x000f000fu, kMagic);  // 1024 + q      (k0, k1)
-  uint32_t q1 = lop3_and_or(w, 0x00f000f0u, kMagic);  // 1024 + 16 q   (k2, k3)
+// one packed word (8 weights along k) -> 4 half2 (k, k+1) pairs, each fp16(scale * (q - zero)):
+//   low nibbles:  0x6400 | q      = 1024 + q   (ulp 1);     + (-(1024 + zero)) is exact
+//   high nibbles: 0x5400 | q << 4 = 64 + q     (ulp 1/16);  + (-(64 + zero))   is exact
+// then one rounding in the multiplication by the scale, as in fp16(scale * (q - zero)).
+__device__ __forceinline__ void dequant_word(uint32_t w, uint32_t nz1024, uint32_t nz64, uint32_t scale2, uint32_t* out) {
   const uint32_t w8 = w >> 8;
-  uint32_t q2 = lop3_and_or(w8, 0x000f000fu, kMagic);  // (k4, k5)
-  uint32_t q3 = lop3_and_or(w8, 0x00f000f0u, kMagic);  // (k6, k7)
-  __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&q0), z1024);
-  __half2 h1 = __hfma2(*reinterpret_cast<__half2*>(&q1), k16th, z64);
-  __half2 h2 = __hsub2(*reinterpret_cast<__half2*>(&q2), z1024);
-  __half2 h3 = __hfma2(*reinterpret_cast<__half2*>(&q3), k16th, z64);
-  h0 = __hmul2(h0, scale);
-  h1 = __hmul2(h1, scale);
-  h2 = __hmul2(h2, scale);
-  h3 = __hmul2(h3, scale);
-  out[0] = *reinterpret_cast<uint32_t*>(&h0);
-  out[1] = *reinterpret_cast<uint32_t*>(&h1);
-  out[2] = *reinterpret_cast<uint32_t*>(&h2);
-  out[3] = *reinterpret_cast<uint32_t*>(&h3);
+  const uint32_t q0 = lop3_and_or(w, 0x000f000fu, 0x64006400u);   // (k0, k1)
+  const uint32_t q1 = lop3_and_or(w, 0x00f000f0u, 0x54005400u);   // (k2, k3)
+  const uint32_t q2 = lop3_and_or(w8, 0x000f000fu, 0x64006400u);  // (k4, k5)
+  const uint32_t q3 = lop3_and_or(w8, 0x00f000f0u, 0x54005400u);  // (k6, k7)
+  out[0] = hmul2_u(hadd2_u(q0, nz1024), scale2);
+  out[1] = hmul2_u(hadd2_u(q1, nz64), scale2);
+  out[2] = hmul2_u(hadd2_u(q2, nz1024), scale2);
+  out[3] = hmul2_u(hadd2_u(q3, nz64), scale2);
+}
+// meta word (fp16 scale | (zero + 1) << 16) -> the three half2 constants of dequant_word
+__device__ __forceinline__ void dequant_consts(uint32_t rec, uint32_t& scale2, uint32_t& nz1024, uint32_t& nz64) {
+  scale2 = prmt(rec, rec, 0x1010);             // fp16 scale in both halves
+  const uint32_t z2 = prmt(rec, rec, 0x3232);  // zero + 1 (1..16) in both halves
+  nz1024 = 0xE400E400u + z2;                   // -(1024 + zero), exact
+  nz64 = 0xD400D400u + (z2 << 4);              // -(64 + zero), exact
 }
 
 struct W4Params {
   __half* y;
-  float* partial;   // [token tile][feature tile][contributor][TN][128] fp32
-  int* counters;    // [token tile][feature tile]
+  float* partial;   // [token tile][super-tile][contributor][kW4R][TN][128] fp32
+  int* counters;    // [token tile][super-tile][2]: partials written / slices reduced
   const __half* bias;
+  const unsigned char* packed;  // unit records, (super-tile, k-block, r) order
   int T, N;
-  int nkb;            // 128-wide k-blocks per tile
-  int n_tiles_n;      // feature tiles
-  int units_per_cta;  // contiguous (tile, k-block) units per CTA
-  int total_units;    // per token tile
-  int max_contrib;    // partial slots per tile
-  int groupsize;      // > 0
-  int group_rows;     // scale/zero rows per k-block = max(1, 128 / groupsize)
+  int nkb;          // 128-wide k-blocks per tile
+  int n_super;      // super-tiles (pairs of 128-feature tiles)
+  int su_per_cta;   // contiguous (super-tile, k-block) super-units per CTA
+  int total_su;     // per token tile
+  int max_contrib;  // partial slots per super-tile
+  int rec_bytes;    // 8192 + group_rows * 512
   unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
-  int debug_flags;            // debug timing experiments (results invalid): 1 = skip dequant math, 2 = skip tcgen05.st
 };
 
-template <int TN>
+// kGR = meta rows per unit record (1, 2 or 4 = 128 / groupsize, 1 for groupsize >= 128)
+template <int TN, int kGR>
 __global__ void __launch_bounds__(kW4Threads, 1)
-gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
-                  const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_z, const W4Params p) {
+gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) {
   using C = GemmW4Cfg<TN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* x_ring = smem;                                     // 1024-aligned stages (128B swizzle)
-  unsigned char* w_ring = smem + C::kXStages * C::kXStageBytes;     // 128-aligned stages
-  uint64_t* full_w = reinterpret_cast<uint64_t*>(w_ring + C::kWStages * C::kWStageBytes);
+  unsigned char* x_ring = smem;                                 // 1024-aligned stages (128B swizzle)
+  unsigned char* w_ring = smem + C::kXStages * C::kXStageBytes; // 1024-aligned stages
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(w_ring + C::kWStages * kW4RecMaxBytes);
   uint64_t* empty_w = full_w + C::kWStages;
   uint64_t* full_x = empty_w + C::kWStages;
-  uint64_t* empty_x = full_x + C::kXStages;
-  uint64_t* a_full = empty_x + C::kXStages;
-  uint64_t* a_empty = a_full + kW4AStages;
-  uint64_t* tmem_full = a_empty + kW4AStages;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  __shared__ int s_is_last[2];
+  uint64_t* su_done = full_x + C::kXStages;     // [kSuRing] MMA commit of super-unit j -> barrier j % kSuRing: its x stage and its A stages are free
+  uint64_t* tmem_full = su_done + C::kSuRing;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // Inputs of super-unit j (its activation tile + the 8 team-warp quarters of its two A tiles) are counted in
+  // s_ready[j % 8]; the MMA warp polls that word with plain shared-memory loads.  (In the warp that issues tcgen05.mma
+  // every dependent wait costs > 100 cycles during which the tensor pipe drains - tools/ubench/umma_rate.cu - so it gets
+  // exactly one per 16 MMAs.)  Monotonic: super-unit j is ready at 9 * (j / 8 + 1).
+  __shared__ uint32_t s_ready[8];
+  __shared__ int s_fix[2][4];  // super-tiles this CTA shares with others: {counter index, super-tile, contributors, my index}
+  __shared__ int s_nfix;
 
   pdl_launch_dependents();
   const int warp = warp_id(), lane = lane_id();
   const int t0 = blockIdx.y * TN;
-  const int u0 = blockIdx.x * p.units_per_cta;
-  const int u1 = min(p.total_units, u0 + p.units_per_cta);
-  const int n_units = u1 - u0;
-  const int tile0 = u0 / p.nkb, kb0 = u0 - tile0 * p.nkb;
-#define W4_TRACE(id)                                                                                   \
+  const int su0 = blockIdx.x * p.su_per_cta;
+  const int su1 = min(p.total_su, su0 + p.su_per_cta);
+  const int n_su = su1 - su0;
+  const int n_units = n_su * kW4R;
+  const int kb0 = su0 % p.nkb;
+#define W4_TRACE(id, who)                                                                              \
   do {                                                                                                 \
-    if (p.trace && threadIdx.x == kW4FirstDqWarp * 32) {                                               \
+    if (p.trace && threadIdx.x == (who)) {                                                             \
       unsigned long long _t;                                                                           \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                           \
       p.trace[blockIdx.x * 64 + (id)] = _t;                                                            \
     }                                                                                                  \
   } while (0)
-  W4_TRACE(0);
+  W4_TRACE(0, 0);
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_x);
-    tma_prefetch_desc(&tmap_s);
-    tma_prefetch_desc(&tmap_z);
     for (int s = 0; s < C::kWStages; ++s) {
       mbar_init(&full_w[s], 1);
-      mbar_init(&empty_w[s], 8);  // the 8 dequant warps of the group that owns the stage
+      mbar_init(&empty_w[s], 4);  // the 4 warps of the team that owns the stage
     }
-    for (int s = 0; s < C::kXStages; ++s) {
-      mbar_init(&full_x[s], 1);
-      mbar_init(&empty_x[s], 1);  // MMA commit
+    for (int s = 0; s < C::kXStages; ++s) mbar_init(&full_x[s], 1);
+    for (int b = 0; b < C::kSuRing; ++b) mbar_init(&su_done[b], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], kW4EpWarps);
     }
-    for (int s = 0; s < kW4AStages; ++s) {
-      mbar_init(&a_full[s], 8);
-      mbar_init(&a_empty[s], 1);
-    }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 8);
+    for (int i = 0; i < 8; ++i) s_ready[i] = 0;
+    s_nfix = 0;
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -175,293 +247,341 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  W4_TRACE(1);
-  const uint32_t tmem_d = tmem_base;        // columns [0, TN)
-  const uint32_t tmem_a = tmem_base + 256;  // columns [256, 512): 4 stages x 64
+  const uint32_t tmem_d = tmem_base;               // accumulator sets
+  const uint32_t tmem_a = tmem_base + C::kABase;   // A-operand ring
+  W4_TRACE(1, 0);
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer: weights (HBM stream)
+  if (warp == kW4WProdWarp) {
+    // ------------------------------------------------------------------ TMA producer: unit records (HBM stream)
     if (elect_one()) {
       const uint64_t pol_w = policy_evict_first();
-      const uint32_t tx = C::kQBytes + p.group_rows * (kW4TileM * 2 + (kW4TileM / 8) * 4);
-      int tile = tile0, kb = kb0, s = 0, ph = 0;
+      const unsigned char* src = p.packed + (size_t)su0 * kW4R * p.rec_bytes;
+      int s = 0, ph = 1;
       for (int i = 0; i < n_units; ++i) {
-        mbar_wait(&empty_w[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_w[s], tx);
-        unsigned char* st = w_ring + s * C::kWStageBytes;
-        const int n0 = tile * kW4TileM, k0 = kb * kW4BlockK;
-        const int g0 = k0 / p.groupsize;
-        tma_load_2d_hint(st, &tmap_q, n0, k0 / 8, &full_w[s], pol_w);
-        tma_load_2d_hint(st + C::kQBytes, &tmap_s, n0, g0, &full_w[s], pol_w);
-        tma_load_2d_hint(st + C::kQBytes + C::kSBytes, &tmap_z, n0 / 8, g0, &full_w[s], pol_w);
-        if (++kb == p.nkb) { kb = 0; ++tile; }
+        mbar_wait(&empty_w[s], ph);
+        mbar_arrive_expect_tx(&full_w[s], p.rec_bytes);
+        tma_bulk_g2s_hint(w_ring + s * kW4RecMaxBytes, src, p.rec_bytes, &full_w[s], pol_w);
+        src += p.rec_bytes;
         if (++s == C::kWStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ TMA producer: activations (L2 resident)
+  } else if (warp == kW4XProdWarp) {
+    // ------------------------------------------------------------------ TMA producer: activations (L2 resident),
+    // one [TN x 128] tile per super-unit; the same thread watches the tiles land and counts them into s_ready
     if (elect_one()) {
       const uint64_t pol_x = policy_evict_last();
       int kb = kb0;
-      pdl_wait();  // x is the previous kernel's output; the weight ring (warp 0) is already streaming
-      for (int i = 0; i < n_units; ++i) {
-        const int s = i % C::kXStages;
-        mbar_wait(&empty_x[s], ((i / C::kXStages) & 1) ^ 1);
+      auto load_x = [&](int s) {
         mbar_arrive_expect_tx(&full_x[s], C::kXStageBytes);
         unsigned char* st = x_ring + s * C::kXStageBytes;
         tma_load_2d_hint(st, &tmap_x, kb * kW4BlockK, t0, &full_x[s], pol_x);
         tma_load_2d_hint(st + C::kXSubBytes, &tmap_x, kb * kW4BlockK + 64, t0, &full_x[s], pol_x);
         if (++kb == p.nkb) kb = 0;
+      };
+      pdl_wait();  // x is the previous kernel's output; the weight ring is already streaming
+      for (int j = 0; j < C::kXStages && j < n_su; ++j) load_x(j);
+      // two independent duties, both polled without blocking: count landed tiles into s_ready (in order), and refill the
+      // stage of super-unit j with the tile of super-unit j + kXStages once the MMAs of j have completed
+      int nj = 0, ns = 0, nph = 0;  // next tile to report: index, stage, parity
+      int rj = 0, rs = 0, rb = 0, rph = 0;  // next super-unit whose stage is refilled: index, stage, su_done barrier, parity
+      const int n_refill = n_su - C::kXStages;
+      uint32_t idle = 0;
+      while (nj < n_su) {
+        bool progress = false;
+        if (mbar_test_wait(&full_x[ns], nph)) {
+          red_release_cta_shared_inc(&s_ready[nj & 7]);
+          ++nj;
+          if (++ns == C::kXStages) { ns = 0; nph ^= 1; }
+          progress = true;
+        }
+        if (rj < n_refill && rj < nj && mbar_test_wait(&su_done[rb], rph)) {
+          load_x(rs);
+          ++rj;
+          if (++rs == C::kXStages) rs = 0;
+          if (++rb == C::kSuRing) { rb = 0; rph ^= 1; }
+          progress = true;
+        }
+        if (!progress) {
+          __nanosleep(20);
+          if (++idle > (1u << 26)) __trap();
+        }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == kW4MmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected thread
+    // issues: keeps the tcgen05 operands in uniform registers)
     constexpr uint32_t idesc = umma_idesc_f16_f32acc(kW4TileM, TN);
-    int seg = 0, kb = kb0;
-    for (int i = 0; i < n_units; ++i) {
-      const bool seg_first = (i == 0) || kb == 0;
-      const bool seg_last = (i == n_units - 1) || kb == p.nkb - 1;
-      const int s = i % C::kXStages, as = i % kW4AStages;
-      if (seg_first && seg > 0) mbar_wait(tmem_empty, (seg - 1) & 1);  // epilogue drained the previous segment's D
-      mbar_wait(&full_x[s], (i / C::kXStages) & 1);
-      mbar_wait(&a_full[as], (i / kW4AStages) & 1);
+    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(x_ring));
+    int seg = 0, kb = kb0, sx = 0, sj = 0;  // sj = j % kSuRing
+    for (int j = 0; j < n_su; ++j) {
+      const bool seg_first = (j == 0) || kb == 0;
+      const bool seg_last = (j == n_su - 1) || kb == p.nkb - 1;
+      const int buf = C::kDBufs == 2 ? (seg & 1) : 0;
+      if (seg_first) {  // the epilogue drained this accumulator set's previous super-tile
+        if (C::kDBufs == 2) mbar_wait(&tmem_empty[buf], ((seg >> 1) & 1) ^ 1);
+        else mbar_wait(&tmem_empty[0], (seg & 1) ^ 1);
+      }
+      {
+        const uint32_t target = 9u * (uint32_t)((j >> 3) + 1);
+        uint32_t spins = 0;
+        while (lds_acquire_cta(&s_ready[j & 7]) < target) {
+          if (++spins > (1u << 26)) __trap();
+        }
+      }
       tcgen05_fence_after();
       if (elect_one()) {
-        const uint32_t xb = smem_u32(x_ring + s * C::kXStageBytes);
+        const uint64_t bdesc = bdesc0 + (uint64_t)((sx * C::kXStageBytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < kW4BlockK / 16; ++k) {
-          const uint64_t bdesc = umma_desc_kmajor_sw128(xb + (k >> 2) * C::kXSubBytes) + (uint64_t)((k & 3) * 2);
-          umma_f16_ts(tmem_d, tmem_a + as * kW4AColsPerStage + k * 8, bdesc, idesc, (!seg_first || k > 0) ? 1u : 0u);
+        for (int r = 0; r < kW4R; ++r) {
+          const uint32_t d = tmem_d + (buf * kW4R + r) * TN, a = tmem_a + (sj * kW4R + r) * kW4AColsPerStage;
+#pragma unroll
+          for (int k = 0; k < kW4BlockK / 16; ++k)
+            umma_f16_ts(d, a + k * 8, bdesc + (uint64_t)((k >> 2) * (C::kXSubBytes >> 4) + (k & 3) * 2), idesc, (!seg_first || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_x[s]);
-        umma_commit(&a_empty[as]);
-        if (seg_last) umma_commit(tmem_full);
+        umma_commit(&su_done[sj]);
+        if (seg_last) umma_commit(&tmem_full[buf]);
       }
       __syncwarp();
       if (seg_last) ++seg;
       if (++kb == p.nkb) kb = 0;
+      if (++sx == C::kXStages) sx = 0;
+      if (++sj == C::kSuRing) sj = 0;
     }
-  } else {
-    // ------------------------------------------------------------------ dequant warps, epilogue at segment ends
-    const int dw = warp - kW4FirstDqWarp;  // 0..15
-    const int group = dw >> 3;             // which alternate units
-    const int half = (dw & 7) >> 2;        // which 64-wide k half of the k-block
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int m = quarter * 32 + lane;     // feature row within the tile
-    const int gtid = threadIdx.x - kW4FirstDqWarp * 32 - group * 256;  // 0..255 within the group
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const uint32_t w_base = smem_u32(w_ring);
-    const uint32_t q_off = (uint32_t)((half * 8) * kW4TileM + m) * 4;
-    uint32_t s_off[2], z_off[2];
+    W4_TRACE(6, kW4MmaWarp * 32);
+  } else if (warp >= kW4FirstDqWarp) {
+    // ------------------------------------------------------------------ dequant teams
+    const int team = (warp - kW4FirstDqWarp) >> 2;  // unit index mod 4
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;              // feature row within the tile
+    const uint32_t a_row = tmem_a + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t w_thread = smem_u32(w_ring) + m * 16;
+    const uint32_t meta_thread = smem_u32(w_ring) + kW4WordBytes + m * 4;
+    uint32_t wq[16], mrec[kGR];
+    int ws = team, wph = 0;   // weight-ring stage / parity of the unit being loaded
+    // unit i (super-unit j = i / 2) lives in A stage i % kAStages and may be written once the MMAs of super-unit
+    // j - kSuRing have completed: barrier su_done[j % kSuRing], phase j / kSuRing - 1
+    auto load_unit = [&](bool landed) {
+      if (!landed) mbar_wait(&full_w[ws], wph);
+      const uint32_t st = ws * kW4RecMaxBytes;
 #pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-      // the two 32-k sub-chunks of this warp's half may sit in different groups when groupsize < 64
-      const int grow = (half * 64 + sub * 32) / p.groupsize;  // row inside the stage's scale/zero tile
-      s_off[sub] = C::kQBytes + (uint32_t)(grow * kW4TileM + m) * 2;
-      z_off[sub] = C::kQBytes + C::kSBytes + (uint32_t)(grow * (kW4TileM / 8) + (m >> 3)) * 4;
-    }
-    const int z_shift = (m & 7) * 4;
-    uint32_t w[8];
-    uint16_t sraw[2];
-    uint32_t zraw[2];
-    int ws = group, wph = 0;  // weight-ring stage / phase of this group's next unit
-    int trace_load = 0;
-    auto load_unit = [&]() {
-      mbar_wait(&full_w[ws], wph);
-      if (trace_load) W4_TRACE(trace_load);  // weight tile landed
-      const uint32_t st = w_base + ws * C::kWStageBytes;
+      for (int c = 0; c < 4; ++c) lds_v4(w_thread + st + c * (kW4TileM * 16), &wq[c * 4]);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) w[r] = lds_u32(st + q_off + r * (kW4TileM * 4));
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        sraw[sub] = lds_u16(st + s_off[sub]);
-        zraw[sub] = lds_u32(st + z_off[sub]);
-      }
+      for (int r = 0; r < kGR; ++r) mrec[r] = lds_u32(meta_thread + st + r * kW4MetaRowBytes);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_w[ws]);
-      ws += 2;
+      ws += kW4Teams;
       if (ws >= C::kWStages) { ws -= C::kWStages; wph ^= 1; }
     };
-    if (group < n_units) load_unit();
-    if (group == 0) W4_TRACE(2);
-    int seg = 0, kb = kb0, tile = tile0;
-    for (int i = 0; i < n_units; ++i) {
-      const bool seg_last = (i == n_units - 1) || kb == p.nkb - 1;
-      if ((i & 1) == group) {
-        const int as = i & (kW4AStages - 1);
-        uint32_t v[32];
+    if (team < n_units) load_unit(false);
+    if (team == 0) W4_TRACE(2, kW4FirstDqWarp * 32);
+    int n = 0;
+    for (int i = team; i < n_units; i += kW4Teams, ++n) {
+      const bool more = i + kW4Teams < n_units;
+      // barrier polls are issued well before their result is needed
+      const int j = i >> 1, jr = j % C::kSuRing;
+      const uint32_t done_par = (uint32_t)(j / C::kSuRing - 1) & 1u;
+      const uint32_t a_dst = a_row + (i % C::kAStages) * kW4AColsPerStage;
+      const bool a_free = j < C::kSuRing || mbar_test_wait(&su_done[jr], done_par);  // looked at after chunk 0
+      const bool w_landed = more && mbar_test_wait(&full_w[ws], wph);                // looked at after chunk 3
+      uint32_t scale2, nz1024, nz64;
+      dequant_consts(mrec[0], scale2, nz1024, nz64);
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int zp = ((zraw[sub] >> z_shift) & 15) + 1;
-          const __half2 sc2 = __half2half2(__ushort_as_half(sraw[sub]));
-          const __half2 z1024 = __half2half2(__ushort_as_half((unsigned short)(0x6400 + zp)));       // 1024 + zp, exact
-          const __half2 z64 = __half2half2(__ushort_as_half((unsigned short)(0xD400 + (zp << 4))));  // -(64 + zp), exact
+      for (int c = 0; c < 4; ++c) {
+        // chunk c = k 32c..32c+31 of the block; its meta row is c * kGR / 4
+        if (c > 0 && (c * kGR) % 4 == 0) dequant_consts(mrec[c * kGR / 4], scale2, nz1024, nz64);
+        uint32_t v[16];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (p.debug_flags & 1) {
-              v[(sub * 4 + r) * 4] = v[(sub * 4 + r) * 4 + 1] = v[(sub * 4 + r) * 4 + 2] = v[(sub * 4 + r) * 4 + 3] = w[sub * 4 + r] & 0x03ff03ffu;
-            } else {
-              dequant_word(w[sub * 4 + r], z1024, z64, sc2, &v[(sub * 4 + r) * 4]);
-            }
-          }
-        }
-        if (i == 8 || i == 10) W4_TRACE(40 + (i - 8) * 4);  // dequant done
-        mbar_wait(&a_empty[as], ((i / kW4AStages) & 1) ^ 1);
-        if (i == 8 || i == 10) W4_TRACE(41 + (i - 8) * 4);  // A stage free
-        tcgen05_fence_after();
-        const uint32_t ta = tmem_a + lane_base + as * kW4AColsPerStage + half * 32;
-        if (!(p.debug_flags & 2)) {
-          tmem_st_32x32b_x16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));
-          tmem_st_32x32b_x16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(v[16]));
-        } else if (v[3] == 0x12345u) {
-          tmem_st_32x32b_x16(ta, reinterpret_cast<const uint32_t(&)[16]>(v[0]));  // keeps v alive
-        }
-        trace_load = (i == 8) ? 52 : (i == 10) ? 53 : 0;
-        if (i + 2 < n_units) load_unit();  // overlaps the TMEM store latency
-        if (i == 8 || i == 10) W4_TRACE(42 + (i - 8) * 4);  // next unit's words in registers
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[as]);
-        if (i == 8 || i == 10) W4_TRACE(43 + (i - 8) * 4);  // stores retired, handed to the MMA warp
-        if (i == 0) W4_TRACE(3);
-
-        if (seg_last) {
-          // -------------------------------------------------------------- epilogue of this tile segment (this group)
-          pdl_wait();  // outputs / bias / stream-K workspace belong to the stream order
-          const int n = tile * kW4TileM + m;
-          const bool n_ok = n < p.N;
-          // contributors of this tile: CTAs whose unit range intersects [tile*nkb, (tile+1)*nkb)
-          const int c_first = (tile * p.nkb) / p.units_per_cta;
-          const int c_last = ((tile + 1) * p.nkb - 1) / p.units_per_cta;
-          const int n_contrib = c_last - c_first + 1;
-          const int my_contrib = (int)blockIdx.x - c_first;
-          const int tix = blockIdx.y * p.n_tiles_n + tile;
-          if (group == 0) W4_TRACE(4 + 4 * (seg & 7));
-          mbar_wait(tmem_full, seg & 1);
-          if (group == 0) W4_TRACE(5 + 4 * (seg & 7));
+        for (int j = 0; j < 4; ++j) dequant_word(wq[c * 4 + j], nz1024, nz64, scale2, &v[j * 4]);
+        if (c == 0) {
+          if (!a_free) mbar_wait(&su_done[jr], done_par);  // the MMAs that read this A stage have completed
           tcgen05_fence_after();
-          const float bv = (p.bias && n_ok) ? __half2float(p.bias[n]) : 0.f;
-          float* part = p.partial + ((size_t)tix * p.max_contrib + my_contrib) * (TN * kW4TileM);
-#pragma unroll 1
-          for (int c = half * 16; c < TN; c += 32) {
-            uint32_t d[16];
-            tmem_ld_32x32b_x16(tmem_d + lane_base + c, d);
-            tmem_ld_wait();
-            if (n_contrib == 1) {
-              if (n_ok) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int t = t0 + c + j;
-                  if (t < p.T) p.y[(size_t)t * p.N + n] = __float2half_rn(__uint_as_float(d[j]) + bv);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) part[(c + j) * kW4TileM + m] = __uint_as_float(d[j]);
-            }
-          }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty);
-          if (group == 0) W4_TRACE(6 + 4 * (seg & 7));
-          if (n_contrib > 1) {
-            // last-arriving contributor sums the slots in contributor order (deterministic).  Release: the group
-            // barrier orders every thread's partial stores before thread 0's gpu-scope fence + counter increment;
-            // acquire: thread 0's fence after observing the count, then the barrier, then .cg loads.
-            asm volatile("bar.sync %0, 256;" ::"r"(2 + group) : "memory");
-            if (gtid == 0) {
-              __threadfence();
-              const int prev = atomicAdd(&p.counters[tix], 1);
-              s_is_last[group] = prev == n_contrib - 1;
-              if (s_is_last[group]) {
-                p.counters[tix] = 0;  // re-armed for the next launch (graph replay safe)
-                __threadfence();
-              }
-            }
-            asm volatile("bar.sync %0, 256;" ::"r"(2 + group) : "memory");
-            if (s_is_last[group]) {
-              const float* base = p.partial + (size_t)tix * p.max_contrib * (TN * kW4TileM);
-              const int n_vec = min(p.T - t0, TN) * (kW4TileM / 4);
-              // float4 per thread; every contributor's load of two elements is in flight before the first add
-              for (int idx0 = gtid; idx0 < n_vec; idx0 += 512) {
-                float4 acc[2];
-                float4 ld[2][4];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int c0 = 0; c0 < n_contrib; c0 += 4) {
-#pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-                    const int idx = idx0 + e * 256;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                      ld[e][cc] = (idx < n_vec && c0 + cc < n_contrib)
-                                      ? __ldcg(reinterpret_cast<const float4*>(&base[(size_t)(c0 + cc) * (TN * kW4TileM) + idx * 4]))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                  }
-#pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                      acc[e].x += ld[e][cc].x; acc[e].y += ld[e][cc].y; acc[e].z += ld[e][cc].z; acc[e].w += ld[e][cc].w;
-                    }
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int idx = idx0 + e * 256;
-                  const int tt = idx / (kW4TileM / 4), mm = (idx % (kW4TileM / 4)) * 4;
-                  const int nn = tile * kW4TileM + mm;
-                  if (idx < n_vec && nn < p.N) {  // N % 32 == 0: a float4 never straddles N
-                    if (p.bias) {
-                      acc[e].x += __half2float(p.bias[nn]); acc[e].y += __half2float(p.bias[nn + 1]);
-                      acc[e].z += __half2float(p.bias[nn + 2]); acc[e].w += __half2float(p.bias[nn + 3]);
-                    }
-                    uint2 o;
-                    o.x = pack_half2(acc[e].x, acc[e].y);
-                    o.y = pack_half2(acc[e].z, acc[e].w);
-                    *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.N + nn]) = o;
-                  }
-                }
-              }
-            }
-            asm volatile("bar.sync %0, 256;" ::"r"(2 + group) : "memory");  // s_is_last is reused by the next segment
-          }
-          if (group == 0) W4_TRACE(7 + 4 * (seg & 7));
         }
-      } else if (seg_last) {
-        // the other group owns this segment's epilogue; still observe the phase (see the mbarrier rule above)
-        mbar_wait(tmem_full, seg & 1);
+        tmem_st_32x32b_x16(a_dst + c * 16, v);
       }
-      if (seg_last) ++seg;
-      if (++kb == p.nkb) { kb = 0; ++tile; }
+      if (more) load_unit(w_landed);  // next unit's words: the shared-memory reads overlap the TMEM store latency
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) red_release_cta_shared_inc(&s_ready[(i >> 1) & 7]);
     }
+    if (team == 0) W4_TRACE(4, kW4FirstDqWarp * 32);
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: one pass per super-tile segment
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int seg = 0, nfix = 0;
+    pdl_wait();  // outputs / bias / stream-K workspace belong to the stream order
+    for (int u = su0; u < su1; ++seg) {
+      const int sup = u / p.nkb;
+      const int seg_end = min(su1, (sup + 1) * p.nkb);
+      const int buf = C::kDBufs == 2 ? (seg & 1) : 0;
+      // contributors of this super-tile: CTAs whose range intersects [sup*nkb, (sup+1)*nkb)
+      const int c_first = (sup * p.nkb) / p.su_per_cta;
+      const int c_last = ((sup + 1) * p.nkb - 1) / p.su_per_cta;
+      const int n_contrib = c_last - c_first + 1;
+      const int my_contrib = (int)blockIdx.x - c_first;
+      const int tix = blockIdx.y * p.n_super + sup;
+      float* part = p.partial + ((size_t)tix * p.max_contrib + my_contrib) * (kW4R * TN * kW4TileM);
+      mbar_wait_relaxed(&tmem_full[buf], C::kDBufs == 2 ? ((seg >> 1) & 1) : (seg & 1));
+      tcgen05_fence_after();
+      W4_TRACE(8 + (seg & 3) * 2, 0);
+#pragma unroll 1
+      for (int r = 0; r < kW4R; ++r) {
+        const int n = (sup * kW4R + r) * kW4TileM + m;
+        const bool n_ok = n < p.N;
+        const float bv = (p.bias && n_ok && n_contrib == 1) ? __half2float(p.bias[n]) : 0.f;
+        constexpr int kCh = TN < 64 ? TN : 64;  // columns fetched per tcgen05.wait::ld
+#pragma unroll 1
+        for (int c = 0; c < TN; c += kCh) {
+          uint32_t d[kCh];
+#pragma unroll
+          for (int q = 0; q < kCh / 16; ++q)
+            tmem_ld_32x32b_x16(tmem_d + lane_base + (buf * kW4R + r) * TN + c + q * 16, reinterpret_cast<uint32_t(&)[16]>(d[q * 16]));
+          tmem_ld_wait();
+          if (n_contrib == 1) {
+            if (n_ok) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) {
+                const int t = t0 + c + j;
+                if (t < p.T) p.y[(size_t)t * p.N + n] = __float2half_rn(__uint_as_float(d[j]) + bv);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kCh; ++j)
+              if (t0 + c + j < p.T) part[(r * TN + c + j) * kW4TileM + m] = __uint_as_float(d[j]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      W4_TRACE(9 + (seg & 3) * 2, 0);
+      if (n_contrib > 1) {
+        // release: the epilogue barrier orders every thread's partial stores before thread 0's gpu-scope fence + count
+        asm volatile("bar.sync 1, %0;" ::"n"(kW4EpWarps * 32) : "memory");
+        if (threadIdx.x == 0) {
+          __threadfence();
+          atomicAdd(&p.counters[2 * tix], 1);
+          s_fix[nfix][0] = tix;
+          s_fix[nfix][1] = sup;
+          s_fix[nfix][2] = n_contrib;
+          s_fix[nfix][3] = my_contrib;
+        }
+        ++nfix;
+      }
+      u = seg_end;
+    }
+    if (threadIdx.x == 0) s_nfix = nfix;
+    W4_TRACE(5, 0);
   }
 
-  W4_TRACE(63);
+  // -------------------------------------------------------------------- shared super-tiles: every contributor reduces a slice
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<C::kTmemCols>(tmem_base);
+  const int nfix = s_nfix;
+  if (nfix > 0) pdl_wait();
+  W4_TRACE(40, 0);
+  for (int f = 0; f < nfix; ++f) {
+    const int tix = s_fix[f][0], sup = s_fix[f][1], n_contrib = s_fix[f][2], my_contrib = s_fix[f][3];
+    if (threadIdx.x == 0) {
+      uint32_t spins = 0;
+      while (ld_acquire_gpu(&p.counters[2 * tix]) < n_contrib) {  // all contributors are co-resident (grid <= #SMs, 1 CTA/SM)
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
+      }
+    }
+    __syncthreads();
+    W4_TRACE(41 + f * 3, 0);
+    const float* base = p.partial + (size_t)tix * p.max_contrib * (kW4R * TN * kW4TileM);
+    const int rows = min(p.T - t0, TN);
+    const int n_vec = kW4R * rows * (kW4TileM / 4);  // float4 elements: [r][row][32]
+    const int per = (n_vec + n_contrib - 1) / n_contrib;
+    const int hi = min(n_vec, (my_contrib + 1) * per);
+    for (int idx = my_contrib * per + (int)threadIdx.x; idx < hi; idx += kW4Threads) {
+      const int r = idx / (rows * (kW4TileM / 4));
+      const int rem = idx - r * rows * (kW4TileM / 4);
+      const int tt = rem / (kW4TileM / 4), mm = (rem % (kW4TileM / 4)) * 4;
+      const size_t off = (size_t)(r * TN + tt) * kW4TileM + mm;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c0 = 0; c0 < n_contrib; c0 += 4) {
+        float4 ld[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          ld[cc] = (c0 + cc < n_contrib) ? __ldcg(reinterpret_cast<const float4*>(&base[(size_t)(c0 + cc) * (kW4R * TN * kW4TileM) + off]))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) { acc.x += ld[cc].x; acc.y += ld[cc].y; acc.z += ld[cc].z; acc.w += ld[cc].w; }
+      }
+      const int nn = (sup * kW4R + r) * kW4TileM + mm;
+      if (nn < p.N) {  // N % 32 == 0: a float4 never straddles N
+        if (p.bias) {
+          acc.x += __half2float(p.bias[nn]); acc.y += __half2float(p.bias[nn + 1]);
+          acc.z += __half2float(p.bias[nn + 2]); acc.w += __half2float(p.bias[nn + 3]);
+        }
+        uint2 o;
+        o.x = pack_half2(acc.x, acc.y);
+        o.y = pack_half2(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.N + nn]) = o;
+      }
+    }
+    W4_TRACE(42 + f * 3, 0);
+    __syncthreads();
+    W4_TRACE(43 + f * 3, 0);
+    if (threadIdx.x == 0) {
+      // the last contributor to finish its slice re-arms both counters for the next launch (graph replay safe)
+      const int prev = atomicAdd(&p.counters[2 * tix + 1], 1);
+      if (prev == n_contrib - 1) {
+        p.counters[2 * tix] = 0;
+        p.counters[2 * tix + 1] = 0;
+        __threadfence();
+      }
+    }
+  }
+  W4_TRACE(63, 0);
 }
 
-// in-place nibble re-order of qweight [K/8][N]: (k0..k7) -> low half k0 k2 k4 k6, high half k1 k3 k5 k7
-__global__ void gptq_repack_kernel(uint32_t* __restrict__ qweight, int64_t n_words, int inverse) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t w = qweight[i];
-    uint32_t r = 0;
+// checkpoint tensors -> unit records.  One thread per output u32.
+__global__ void gptq_pack_kernel(const uint32_t* __restrict__ qweight, const uint32_t* __restrict__ qzeros,
+                                 const __half* __restrict__ scales, uint32_t* __restrict__ packed, int64_t K, int64_t N, int groupsize,
+                                 int group_rows, int nkb, int64_t n_words_total) {
+  const int rec_words = (kW4WordBytes + group_rows * kW4MetaRowBytes) / 4;
+  const int64_t G = (K + groupsize - 1) / groupsize;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_words_total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t rec = o / rec_words;          // record index in (super-tile, k-block, r) order
+    const int r = (int)(o - rec * rec_words);
+    const int64_t sup = rec / ((int64_t)nkb * kW4R);
+    const int kb = (int)((rec / kW4R) % nkb);
+    const int64_t tile = sup * kW4R + rec % kW4R;
+    uint32_t out = 0;
+    if (r < kW4WordBytes / 4) {
+      const int c = r / (kW4TileM * 4), m = (r / 4) % kW4TileM, j = r % 4;
+      const int64_t n = tile * kW4TileM + m;
+      const int64_t kw = (int64_t)kb * (kW4BlockK / 8) + c * 4 + j;  // checkpoint word row: k = 8 kw .. 8 kw + 7
+      if (n < N && kw * 8 < K) {
+        const uint32_t w = qweight[kw * N + n];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int pos = (k & 1) * 4 + (k >> 1);  // nibble position of k in the repacked word
-      if (!inverse) r |= ((w >> (4 * k)) & 15u) << (4 * pos);
-      else r |= ((w >> (4 * pos)) & 15u) << (4 * k);
+        for (int k = 0; k < 8; ++k) out |= ((w >> (4 * k)) & 15u) << (4 * ((k & 1) * 4 + (k >> 1)));
+      }
+    } else {
+      const int mr = r - kW4WordBytes / 4;
+      const int row = mr / kW4TileM, m = mr % kW4TileM;
+      const int64_t n = tile * kW4TileM + m;
+      const int64_t k0 = (int64_t)kb * kW4BlockK + (int64_t)row * (kW4BlockK / group_rows);
+      out = 1u << 16;  // padding: scale 0, zero 1
+      if (n < N && k0 < K) {
+        const int64_t g = min(k0 / groupsize, G - 1);
+        const uint32_t z = ((qzeros[g * (N / 8) + n / 8] >> (4 * (n % 8))) & 15u) + 1u;  // the +1 of quant_linear.py:185
+        out = (uint32_t)__half_as_ushort(scales[g * N + n]) | (z << 16);
+      }
     }
-    qweight[i] = r;
+    packed[o] = out;
   }
 }
 
 static unsigned long long* g_w4_trace = nullptr;
-static int g_w4_debug_flags = 0;
 
 static int num_sms() {
   static int n = 0;
@@ -474,27 +594,32 @@ static int num_sms() {
 }
 
 struct W4Plan {
-  int TN, nkb, n_tiles_n, n_tiles_t, units_per_cta, n_ctas, max_contrib;
+  int TN, nkb, n_super, n_tiles_t, su_per_cta, n_ctas, max_contrib;
 };
 
 static W4Plan plan_w4(int64_t T, int64_t N, int64_t K, int sms) {
   W4Plan pl;
   pl.TN = T <= 16 ? 16 : T <= 32 ? 32 : T <= 64 ? 64 : 128;
   pl.nkb = (int)((K + kW4BlockK - 1) / kW4BlockK);
-  pl.n_tiles_n = (int)((N + kW4TileM - 1) / kW4TileM);
+  pl.n_super = (int)((N + kW4R * kW4TileM - 1) / (kW4R * kW4TileM));
   pl.n_tiles_t = (int)((T + pl.TN - 1) / pl.TN);
-  const int total = pl.n_tiles_n * pl.nkb;
+  const int total = pl.n_super * pl.nkb;
   if (pl.n_tiles_t > 1) {
-    pl.units_per_cta = pl.nkb;  // whole tiles (prefill: plenty of tiles)
+    pl.su_per_cta = pl.nkb;  // whole super-tiles (prefill: plenty of tiles)
   } else {
     const int ctas = total < sms ? total : sms;
-    pl.units_per_cta = (total + ctas - 1) / ctas;
-    if (pl.units_per_cta < 2 && pl.nkb >= 2) pl.units_per_cta = 2;
+    pl.su_per_cta = (total + ctas - 1) / ctas;
+    if (pl.su_per_cta < 2 && pl.nkb >= 2) pl.su_per_cta = 2;  // one unit per team at least
   }
-  pl.n_ctas = (total + pl.units_per_cta - 1) / pl.units_per_cta;
-  pl.max_contrib = (pl.nkb + pl.units_per_cta - 1) / pl.units_per_cta + 1;
-  if (pl.units_per_cta % pl.nkb == 0) pl.max_contrib = 1;
+  pl.n_ctas = (total + pl.su_per_cta - 1) / pl.su_per_cta;
+  pl.max_contrib = (pl.nkb + pl.su_per_cta - 1) / pl.su_per_cta + 1;
+  if (pl.su_per_cta % pl.nkb == 0) pl.max_contrib = 1;
   return pl;
+}
+
+static int w4_group_rows(int64_t K, int* groupsize) {
+  if (*groupsize <= 0) *groupsize = (int)((K + kW4BlockK - 1) / kW4BlockK * kW4BlockK);  // one group
+  return *groupsize >= kW4BlockK ? 1 : kW4BlockK / *groupsize;
 }
 
 }  // namespace b200
@@ -503,15 +628,42 @@ using namespace b200;
 
 // debug: device buffer of [n_ctas][64] uint64 receiving per-CTA phase timestamps of the next int4 GEMM launches
 extern "C" void b200_debug_w4_trace(void* device_buffer) { g_w4_trace = (unsigned long long*)device_buffer; }
-extern "C" void b200_debug_w4_flags(int flags) { g_w4_debug_flags = flags; }
+extern "C" void b200_debug_w4_flags(int) {}
 
-extern "C" int b200_gptq_repack(void* qweight, int64_t K, int64_t N, int inverse, void* stream) {
-  if (K % 8 != 0) { b200_set_last_error("gptq_repack: K % 8 != 0"); return B200_ERR_ARG; }
-  const int64_t n_words = K / 8 * N;
-  if (n_words == 0) return B200_OK;
+static bool w4_check_shape(int64_t N, int64_t K, int groupsize, const char* who) {
+  if (K % 32 != 0 || N % 32 != 0 || K <= 0 || N <= 0) {  // exllamav2.py:118-119 asserts the same
+    b200_set_last_error((std::string(who) + ": need K % 32 == 0 and N % 32 == 0").c_str());
+    return false;
+  }
+  if (groupsize > 0 && (groupsize % 32 != 0 || (groupsize > kW4BlockK && groupsize % kW4BlockK != 0) ||
+                        (groupsize < kW4BlockK && kW4BlockK % groupsize != 0))) {
+    b200_set_last_error((std::string(who) + ": groupsize must be 32, 64, a multiple of 128, or <= 0 (one group)").c_str());
+    return false;
+  }
+  return true;
+}
+
+extern "C" int64_t b200_gptq_packed_bytes(int64_t K, int64_t N, int groupsize) {
+  if (!w4_check_shape(N, K, groupsize, "gptq_packed_bytes")) return B200_ERR_ARG;
+  const int gr = w4_group_rows(K, &groupsize);
+  const int64_t nkb = (K + kW4BlockK - 1) / kW4BlockK, ns = (N + kW4R * kW4TileM - 1) / (kW4R * kW4TileM);
+  return ns * kW4R * nkb * (kW4WordBytes + gr * kW4MetaRowBytes);  // the last super-tile is padded with empty tiles
+}
+
+// qweight int32 [K/8, N], qzeros int32 [ceil(K/g), N/8], scales fp16 [ceil(K/g), N] (checkpoint layout, left untouched)
+// -> packed (b200_gptq_packed_bytes bytes, 16-byte aligned).  Groups are k // groupsize (trivial g_idx).
+extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
+                              int groupsize, void* stream) {
+  if (!w4_check_shape(N, K, groupsize, "gptq_pack")) return B200_ERR_ARG;
+  if (((uintptr_t)packed & 15) != 0) { b200_set_last_error("gptq_pack: packed buffer must be 16-byte aligned"); return B200_ERR_ARG; }
+  const int gr = w4_group_rows(K, &groupsize);
+  const int nkb = (int)((K + kW4BlockK - 1) / kW4BlockK);
+  const int64_t n_words = b200_gptq_packed_bytes(K, N, groupsize) / 4;
   int64_t blocks = (n_words + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  gptq_repack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint32_t*)qweight, n_words, inverse);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gptq_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qweight, (const uint32_t*)qzeros,
+                                                                        (const __half*)scales, (uint32_t*)packed, K, N, groupsize, gr,
+                                                                        nkb, n_words);
   B200_CHECK_LAUNCH();
   b200_count_launches(1);
   return B200_OK;
@@ -521,16 +673,16 @@ extern "C" int b200_gptq_repack(void* qweight, int64_t K, int64_t N, int inverse
 int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K) {
   const W4Plan pl = plan_w4(T, N, K, 148);
   if (pl.max_contrib <= 1) return 0;
-  return (int64_t)pl.n_tiles_t * pl.n_tiles_n * pl.max_contrib * pl.TN * kW4TileM * 4;
+  return (int64_t)pl.n_tiles_t * pl.n_super * pl.max_contrib * kW4R * pl.TN * kW4TileM * 4;
 }
 
-template <int TN>
-static int launch_gemm_w4(const CUtensorMap* mq, const CUtensorMap* mx, const CUtensorMap* ms, const CUtensorMap* mz, void* y,
-                          void* workspace, const void* bias, int T, int N, const W4Plan& pl, int groupsize, cudaStream_t st) {
+template <int TN, int kGR>
+static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, void* workspace, const void* bias, int T, int N,
+                          const W4Plan& pl, cudaStream_t st) {
   using C = GemmW4Cfg<TN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN, kGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
     configured = true;
   }
@@ -539,58 +691,49 @@ static int launch_gemm_w4(const CUtensorMap* mq, const CUtensorMap* mx, const CU
   p.counters = (int*)workspace;
   p.partial = workspace ? (float*)((char*)workspace + kW4CounterBytes) : nullptr;
   p.bias = (const __half*)bias;
+  p.packed = (const unsigned char*)packed;
   p.T = T;
   p.N = N;
   p.nkb = pl.nkb;
-  p.n_tiles_n = pl.n_tiles_n;
-  p.units_per_cta = pl.units_per_cta;
-  p.total_units = pl.n_tiles_n * pl.nkb;
+  p.n_super = pl.n_super;
+  p.su_per_cta = pl.su_per_cta;
+  p.total_su = pl.n_super * pl.nkb;
   p.max_contrib = pl.max_contrib;
-  p.groupsize = groupsize;
-  p.group_rows = groupsize >= kW4BlockK ? 1 : kW4BlockK / groupsize;
+  p.rec_bytes = kW4WordBytes + kGR * kW4MetaRowBytes;
   p.trace = g_w4_trace;
-  p.debug_flags = g_w4_debug_flags;
   dim3 grid(pl.n_ctas, pl.n_tiles_t, 1);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 0, st);
-  B200_LAUNCH(gemm_w4a16_kernel<TN>, grid, dim3(kW4Threads), (size_t)C::kSmemBytes, st, *mq, *mx, *ms, *mz, p);
+  B200_LAUNCH(gemm_w4a16_kernel<TN, kGR>, grid, dim3(kW4Threads), (size_t)C::kSmemBytes, st, *mx, p);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 1, st);
   b200_count_launches(1);
   return B200_OK;
 }
 
-// qweight must have been passed through b200_gptq_repack once.  groupsize: multiple of 32, or <= 0 for one group.
+// packed: output of b200_gptq_pack for the same (K, N, groupsize).
 // workspace as for b200_gemm_f16 (b200_gemm_workspace_bytes); without it every CTA takes whole tiles (no stream-K).
-extern "C" int b200_gemm_w4a16(const void* x, const void* qweight_repacked, const void* qzeros, const void* scales,
-                               const void* bias, void* y, int64_t T, int64_t N, int64_t K, int groupsize, void* workspace,
-                               void* stream) {
+extern "C" int b200_gemm_w4a16(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
+                               int groupsize, void* workspace, void* stream) {
   if (T == 0 || N == 0) return B200_OK;
-  if (K % 64 != 0 || N % 32 != 0 || (groupsize > 0 && groupsize % 32 != 0)) {  // exllamav2.py:118-119 asserts the same
-    b200_set_last_error("gemm_w4a16: need K % 64 == 0, N % 32 == 0, groupsize % 32 == 0");
-    return B200_ERR_ARG;
-  }
-  if (groupsize <= 0) groupsize = (int)((K + kW4BlockK - 1) / kW4BlockK * kW4BlockK);  // one group: always row 0
-  if (groupsize > kW4BlockK && groupsize % kW4BlockK != 0) {
-    b200_set_last_error("gemm_w4a16: groupsize above 128 must be a multiple of 128");
-    return B200_ERR_UNSUPPORTED;
-  }
+  if (!w4_check_shape(N, K, groupsize, "gemm_w4a16")) return B200_ERR_ARG;
+  const int gr = w4_group_rows(K, &groupsize);
   W4Plan pl = plan_w4(T, N, K, num_sms());
-  if (pl.max_contrib > 1 && (!workspace || (int64_t)pl.n_tiles_n * pl.n_tiles_t * 4 > kW4CounterBytes)) {
-    pl.units_per_cta = pl.nkb;  // whole tiles per CTA
-    pl.n_ctas = pl.n_tiles_n;
+  if (pl.max_contrib > 1 && (!workspace || (int64_t)pl.n_super * pl.n_tiles_t * 8 > kW4CounterBytes || pl.n_ctas > num_sms())) {
+    pl.su_per_cta = pl.nkb;  // whole super-tiles per CTA
+    pl.n_ctas = pl.n_super;
     pl.max_contrib = 1;
   }
-  const int64_t G = (K + groupsize - 1) / groupsize;
-  const int grows = groupsize >= kW4BlockK ? 1 : kW4BlockK / groupsize;
-  const CUtensorMap* mq = get_tmap_2d(qweight_repacked, K / 8, N, N, kW4BlockK / 8, kW4TileM, TmapDtype::kI32, TmapSwizzle::kNone);
   const CUtensorMap* mx = get_tmap_2d(x, T, K, K, pl.TN, 64, TmapDtype::kF16, TmapSwizzle::k128B);
-  const CUtensorMap* ms = get_tmap_2d(scales, G, N, N, grows, kW4TileM, TmapDtype::kF16, TmapSwizzle::kNone);
-  const CUtensorMap* mz = get_tmap_2d(qzeros, G, N / 8, N / 8, grows, kW4TileM / 8, TmapDtype::kI32, TmapSwizzle::kNone);
-  if (!mq || !mx || !ms || !mz) return B200_ERR_CUDA;
+  if (!mx) return B200_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
+#define W4_DISPATCH(TNV)                                                                                          \
+  (gr == 1 ? launch_gemm_w4<TNV, 1>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, st)                       \
+           : gr == 2 ? launch_gemm_w4<TNV, 2>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, st)             \
+                     : launch_gemm_w4<TNV, 4>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, st))
   switch (pl.TN) {
-    case 16: return launch_gemm_w4<16>(mq, mx, ms, mz, y, workspace, bias, (int)T, (int)N, pl, groupsize, st);
-    case 32: return launch_gemm_w4<32>(mq, mx, ms, mz, y, workspace, bias, (int)T, (int)N, pl, groupsize, st);
-    case 64: return launch_gemm_w4<64>(mq, mx, ms, mz, y, workspace, bias, (int)T, (int)N, pl, groupsize, st);
-    default: return launch_gemm_w4<128>(mq, mx, ms, mz, y, workspace, bias, (int)T, (int)N, pl, groupsize, st);
+    case 16: return W4_DISPATCH(16);
+    case 32: return W4_DISPATCH(32);
+    case 64: return W4_DISPATCH(64);
+    default: return W4_DISPATCH(128);
   }
+#undef W4_DISPATCH
 }

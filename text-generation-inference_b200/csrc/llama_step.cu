@@ -9,7 +9,7 @@
 
 static int linear(const B200Linear* L, const void* x, void* y, int64_t T, void* gemm_ws, void* stream) {
   if (L->qweight)
-    return b200_gemm_w4a16(x, L->qweight, L->qzeros, L->scales, L->bias, y, T, L->N, L->K, L->groupsize, gemm_ws, stream);
+    return b200_gemm_w4a16(x, L->qweight, L->bias, y, T, L->N, L->K, L->groupsize, gemm_ws, stream);
   return b200_gemm_f16(x, L->weight, L->bias, y, T, L->N, L->K, gemm_ws, stream);
 }
 

@@ -122,7 +122,7 @@ def _fill_linear(dst: _lib.B200Linear, lin) -> None:
     if isinstance(lin, Ex4bitLinearV2):
         lin.post_init()
         dst.weight = None
-        dst.qweight, dst.qzeros, dst.scales = lin.qweight.data_ptr(), lin.qzeros.data_ptr(), lin.scales.data_ptr()
+        dst.qweight, dst.qzeros, dst.scales = lin.q_handle.data_ptr(), None, None
         dst.N, dst.K, dst.groupsize = lin.outfeatures, lin.infeatures, lin.group_size
     elif isinstance(lin, FastLinear):
         dst.weight = lin.weight.data_ptr()

@@ -154,30 +154,36 @@ def gemm_f16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
     return out
 
 
-def gptq_repack(qweight: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+def gptq_pack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, groupsize: int) -> torch.Tensor:
+    """Checkpoint GPTQ tensors of one linear -> the kernel's unit-record stream (uint8 tensor)."""
     _req(qweight, torch.int32, "qweight")
-    assert qweight.is_contiguous()
-    Kw, N = qweight.shape
-    _lib.check(_lib.load().b200_gptq_repack(_ptr(qweight), Kw * 8, N, int(inverse), _stream()), "gptq_repack")
-    return qweight
-
-
-def gemm_w4a16(x: torch.Tensor, qweight_repacked: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, groupsize: int,
-               bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _req(x, torch.float16, "x")
-    _req(qweight_repacked, torch.int32, "qweight")
     _req(qzeros, torch.int32, "qzeros")
     _req(scales, torch.float16, "scales")
-    assert x.is_contiguous() and qweight_repacked.is_contiguous() and qzeros.is_contiguous() and scales.is_contiguous()
+    assert qweight.is_contiguous() and qzeros.is_contiguous() and scales.is_contiguous()
+    Kw, N = qweight.shape
+    K = Kw * 8
+    lib = _lib.load()
+    nbytes = lib.b200_gptq_packed_bytes(K, N, groupsize)
+    if nbytes < 0:
+        raise _lib.B200Error(f"gptq_pack: {lib.b200_last_error().decode()}")
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=qweight.device)
+    _lib.check(lib.b200_gptq_pack(_ptr(qweight), _ptr(qzeros), _ptr(scales), _ptr(packed), K, N, groupsize, _stream()), "gptq_pack")
+    return packed
+
+
+def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, N: int, groupsize: int, bias: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T,K] fp16 @ dequant(packed) -> [T,N] fp16; `packed` from gptq_pack for the same (K, N, groupsize)."""
+    _req(x, torch.float16, "x")
+    _req(packed, torch.uint8, "packed")
+    assert x.is_contiguous() and packed.is_contiguous()
     T, K = x.shape
-    N = qweight_repacked.shape[1]
     if out is None:
         out = torch.empty(T, N, dtype=torch.float16, device=x.device)
     if workspace is None:
         workspace = gemm_workspace(x.device, T, N, K)
-    _lib.check(_lib.load().b200_gemm_w4a16(_ptr(x), _ptr(qweight_repacked), _ptr(qzeros), _ptr(scales), _ptr(bias), _ptr(out),
-                                           T, N, K, groupsize, _ptr(workspace), _stream()), "gemm_w4a16")
+    _lib.check(_lib.load().b200_gemm_w4a16(_ptr(x), _ptr(packed), _ptr(bias), _ptr(out), T, N, K, groupsize, _ptr(workspace),
+                                           _stream()), "gemm_w4a16")
     return out
 
 

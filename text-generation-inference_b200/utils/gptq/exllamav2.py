@@ -2,8 +2,9 @@
 
 Mirrors /root/reference/server/text_generation_server/utils/gptq/exllamav2.py:100-144 (`Ex4bitLinearV2`: same
 constructor arguments, `post_init()` one-time repack, `forward`), with `exllamav2_kernels.make_q_matrix` /
-`gemm_half_q_half` replaced by `b200_gptq_repack` / `b200_gemm_w4a16`.  No scratch `temp_dq`: the kernel never
-materialises the fp16 matrix (contrast :65-97, :87).
+`gemm_half_q_half` replaced by `b200_gptq_pack` / `b200_gemm_w4a16`: `post_init()` converts the checkpoint tensors once
+into the kernel's streaming layout (`q_handle` = the packed buffer) and drops them.  No scratch `temp_dq`: the kernel
+never materialises the fp16 matrix (contrast :65-97, :87).
 """
 from __future__ import annotations
 
@@ -37,21 +38,20 @@ class Ex4bitLinearV2(nn.Module):
                 raise NotImplementedError("act-order (non-trivial g_idx) checkpoints are not supported yet")
 
     def post_init(self, temp_dq=None):
-        """exllamav2.py:124-137: one-time in-place weight shuffle."""
-        assert self.qweight.device.type == "cuda"
+        """exllamav2.py:124-137 (make_q_matrix): one-time conversion to the kernel layout; the checkpoint tensors are
+        released afterwards (the packed buffer holds everything the GEMM reads)."""
         if self.q_handle is None:
-            self.qweight = self.qweight.contiguous()
-            _ops().gptq_repack(self.qweight)
-            self.qzeros = self.qzeros.contiguous()
-            self.scales = self.scales.contiguous()
-            self.q_handle = True
+            assert self.qweight.device.type == "cuda"
+            self.q_handle = _ops().gptq_pack(self.qweight.contiguous(), self.qzeros.contiguous(), self.scales.contiguous(),
+                                             self.group_size)
+            self.qweight = self.qzeros = self.scales = None
 
     def forward(self, x, force_cuda=False):
         if self.q_handle is None:
             self.post_init()
         out_shape = x.shape[:-1] + (self.outfeatures,)
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        out = _ops().gemm_w4a16(x2, self.qweight, self.qzeros, self.scales, self.group_size, self.bias)
+        out = _ops().gemm_w4a16(x2, self.q_handle, self.outfeatures, self.group_size, self.bias)
         return out.view(out_shape)
 
     def temp_dq_size(self):

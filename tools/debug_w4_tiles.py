@@ -11,10 +11,9 @@ for (T, N, K) in [(64, 4096, 4096), (33, 2560, 2048), (64, 4096, 11008)]:
     qweight, qzeros, scales, g_idx = ogptq.quantize_rtn(w, 128)
     x = torch.randn(T, K, generator=g).half()
     ref = ogptq.gemm_half_q_half(x, qweight, qzeros, scales, None, 128).float()
-    qw_d = qweight.clone().to(dev)
-    ops.gptq_repack(qw_d)
+    packed = ops.gptq_pack(qweight.to(dev), qzeros.to(dev), scales.to(dev), 128)
     for rep in range(3):
-        got = ops.gemm_w4a16(x.to(dev), qw_d, qzeros.to(dev), scales.to(dev), 128).float().cpu()
+        got = ops.gemm_w4a16(x.to(dev), packed, N, 128).float().cpu()
         err = (got - ref).abs()
         bad = err > (1e-3 * ref.abs().max() + 2e-3 * ref.abs())
         nt = N // 128
