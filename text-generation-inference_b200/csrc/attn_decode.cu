@@ -14,6 +14,8 @@
 // The kernel is bandwidth-bound: algorithmic bytes = 2 * L * d * 2 B per (sequence, kv head).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b200 {
 
 constexpr int kMaxChunkTokens = 512;  // <= 32 pages: the producer warp holds one block id per lane
@@ -297,12 +299,24 @@ extern "C" int b200_attn_decode_paged(const void* q, int64_t q_token_stride, con
     return B200_ERR_ARG;
   }
   if ((q_token_stride & 1) || ((uintptr_t)q & 3)) { b200_set_last_error("attn_decode_paged: q must be 4-byte aligned"); return B200_ERR_ARG; }
-  // split-KV granularity: the largest chunk that still gives every SM several CTAs (2 resident CTAs x 148 SMs)
-  int chunk_tokens = kMaxChunkTokens;
-  while (chunk_tokens > kMinChunkTokens &&
-         (int64_t)B * n_kv_heads * ((max_context_len + chunk_tokens - 1) / chunk_tokens) < 4 * 296)
-    chunk_tokens >>= 1;
-  int n_chunks = (max_context_len + chunk_tokens - 1) / chunk_tokens;
+  // split-KV granularity: the largest chunk size that still gives every SM several CTAs (2 resident CTAs x 148 SMs), then
+  // EQUAL chunks of that count (page aligned): with a fixed 512 a context of 1563 tokens would be cut 512/512/512/27 and the
+  // last quarter of the CTAs would do almost nothing while the others set the kernel's duration
+  int target = kMaxChunkTokens;
+  {
+    static int env_target = -1;
+    if (env_target < 0) {
+      const char* e = getenv("B200_ATTN_CHUNK");
+      env_target = e ? atoi(e) : 0;
+    }
+    if (env_target >= kMinChunkTokens && env_target <= kMaxChunkTokens) target = env_target;
+  }
+  while (target > kMinChunkTokens && (int64_t)B * n_kv_heads * ((max_context_len + target - 1) / target) < 4 * 296) target >>= 1;
+  int n_chunks = (max_context_len + target - 1) / target;
+  if (n_chunks < 1) n_chunks = 1;
+  int chunk_tokens = ((max_context_len + n_chunks - 1) / n_chunks + kPageTokens - 1) / kPageTokens * kPageTokens;
+  if (chunk_tokens < kMinChunkTokens) chunk_tokens = kMinChunkTokens;
+  n_chunks = (max_context_len + chunk_tokens - 1) / chunk_tokens;
   if (n_chunks < 1) n_chunks = 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (head_dim == 128)

@@ -52,10 +52,10 @@ constexpr int kW4RecMaxBytes = kW4WordBytes + kW4MaxGroupRows * kW4MetaRowBytes;
 constexpr int kW4Teams = 4;
 constexpr int kW4EpWarps = 4;                                   // warps 0..3
 constexpr int kW4FirstDqWarp = kW4EpWarps;                      // warps 4..19
-constexpr int kW4MmaWarp = kW4FirstDqWarp + 4 * kW4Teams;       // 20
-constexpr int kW4WProdWarp = kW4MmaWarp + 1;                    // 21
-constexpr int kW4XProdWarp = kW4MmaWarp + 2;                    // 22
-constexpr int kW4Threads = (kW4XProdWarp + 1) * 32;             // 736
+constexpr int kW4MmaWarp = kW4FirstDqWarp + 4 * kW4Teams;       // 20, 21: two MMA warps taking alternate super-units
+constexpr int kW4WProdWarp = kW4MmaWarp + 2;                    // 22
+constexpr int kW4XProdWarp = kW4MmaWarp + 3;                    // 23
+constexpr int kW4Threads = (kW4XProdWarp + 1) * 32;             // 768
 constexpr int kW4AColsPerStage = 64;  // 128 fp16 per row = 64 x 32-bit columns
 constexpr int64_t kW4CounterBytes = 64 * 1024;
 
@@ -205,6 +205,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
   // every dependent wait costs > 100 cycles during which the tensor pipe drains - tools/ubench/umma_rate.cu - so it gets
   // exactly one per 16 MMAs.)  Monotonic: super-unit j is ready at 9 * (j / 8 + 1).
   __shared__ uint32_t s_ready[8];
+  __shared__ uint32_t s_issued;  // super-units whose MMAs have been issued (hand-over between the two MMA warps)
   __shared__ int s_fix[2][4];  // super-tiles this CTA shares with others: {counter index, super-tile, contributors, my index}
   __shared__ int s_nfix;
 
@@ -239,6 +240,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
       mbar_init(&tmem_empty[b], kW4EpWarps);
     }
     for (int i = 0; i < 8; ++i) s_ready[i] = 0;
+    s_issued = 0;
     s_nfix = 0;
     mbar_fence_init();
   }
@@ -307,24 +309,37 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
         }
       }
     }
-  } else if (warp == kW4MmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected thread
-    // issues: keeps the tcgen05 operands in uniform registers)
+  } else if (warp == kW4MmaWarp || warp == kW4MmaWarp + 1) {
+    // ------------------------------------------------------------------ MMA issuers.  tcgen05.mma issue is in order and the
+    // queue is shallow, so a warp that has just issued 16 MMAs cannot hide its own bookkeeping (barrier polls, commit)
+    // behind them: the tensor pipe would idle ~40 % of the time (tools/ubench/umma_rate.cu).  Two warps take alternate
+    // super-units; while one is blocked issuing, the other has already found its inputs ready and only waits for its turn
+    // (s_issued), so MMAs reach the pipe back to back and in super-unit order (summation order stays fixed).
+    // Warp-uniform loops, one elected thread issues: keeps the tcgen05 operands in uniform registers.
+    const int me = warp - kW4MmaWarp;
     constexpr uint32_t idesc = umma_idesc_f16_f32acc(kW4TileM, TN);
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(x_ring));
-    int seg = 0, kb = kb0, sx = 0, sj = 0;  // sj = j % kSuRing
-    for (int j = 0; j < n_su; ++j) {
+    for (int j = me; j < n_su; j += 2) {
+      const int kbj = kb0 + j;            // k-block index counted from the CTA's first super-tile
+      const int kb = kbj % p.nkb, seg = kbj / p.nkb;
       const bool seg_first = (j == 0) || kb == 0;
       const bool seg_last = (j == n_su - 1) || kb == p.nkb - 1;
       const int buf = C::kDBufs == 2 ? (seg & 1) : 0;
+      const int sx = j % C::kXStages, sj = j % C::kSuRing;
+      {
+        const uint32_t target = 9u * (uint32_t)((j >> 3) + 1);
+        uint32_t spins = 0;
+        while (lds_acquire_cta(&s_ready[j & 7]) < target) {
+          if (++spins > (1u << 26)) __trap();
+        }
+      }
       if (seg_first) {  // the epilogue drained this accumulator set's previous super-tile
         if (C::kDBufs == 2) mbar_wait(&tmem_empty[buf], ((seg >> 1) & 1) ^ 1);
         else mbar_wait(&tmem_empty[0], (seg & 1) ^ 1);
       }
       {
-        const uint32_t target = 9u * (uint32_t)((j >> 3) + 1);
         uint32_t spins = 0;
-        while (lds_acquire_cta(&s_ready[j & 7]) < target) {
+        while (lds_acquire_cta(&s_issued) < (uint32_t)j) {  // my turn
           if (++spins > (1u << 26)) __trap();
         }
       }
@@ -338,14 +353,11 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
           for (int k = 0; k < kW4BlockK / 16; ++k)
             umma_f16_ts(d, a + k * 8, bdesc + (uint64_t)((k >> 2) * (C::kXSubBytes >> 4) + (k & 3) * 2), idesc, (!seg_first || k > 0) ? 1u : 0u);
         }
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&s_issued)), "r"((uint32_t)j + 1) : "memory");
         umma_commit(&su_done[sj]);
         if (seg_last) umma_commit(&tmem_full[buf]);
       }
       __syncwarp();
-      if (seg_last) ++seg;
-      if (++kb == p.nkb) kb = 0;
-      if (++sx == C::kXStages) sx = 0;
-      if (++sj == C::kSuRing) sj = 0;
     }
     W4_TRACE(6, kW4MmaWarp * 32);
   } else if (warp >= kW4FirstDqWarp) {
@@ -506,7 +518,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
       const int tt = rem / (kW4TileM / 4), mm = (rem % (kW4TileM / 4)) * 4;
       const size_t off = (size_t)(r * TN + tt) * kW4TileM + mm;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c0 = 0; c0 < n_contrib; c0 += 4) {
+      for (int c0 = 0; c0 < n_contrib; c0 += 4) {  // contributor order: deterministic
         float4 ld[4];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)
