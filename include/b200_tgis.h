@@ -116,11 +116,21 @@ int b200_gemm_f16(const void* x, const void* w, const void* bias, void* y, int64
 int64_t b200_gptq_packed_bytes(int64_t K, int64_t N, int groupsize);
 int b200_gptq_pack(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
                    int groupsize, void* stream);
+/* layout 0 = b200_gptq_pack.  layout 1 ("gate|up", N = 2 I with I % 128 == 0): the records of gate feature tile s and of
+ * up feature tile s are adjacent, for the fused [gate; up] projection of LlamaMLP (flash_llama_modeling.py:315-335). */
+#define B200_W4_LAYOUT_PLAIN 0
+#define B200_W4_LAYOUT_GATE_UP 1
+int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
+                      int groupsize, int layout, void* stream);
 
 /* y[T,N] = x[T,K] . dequant(packed) (+ bias);  replaces exllamav2_kernels.gemm_half_q_half
  * (utils/gptq/exllamav2.py:14-20) for every T (no dequant-to-scratch branch, cf. :87). */
 int b200_gemm_w4a16(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
                     int groupsize, void* workspace, void* stream);
+/* same for a weight packed with `layout`; act = 1 (layout 1 only) additionally replaces `act(gu[:, 0]) * gu[:, 1]`
+ * (flash_llama_modeling.py:332-335, with b200_silu_mul's arithmetic): y is [T, N/2] = SiLU(x Wgate) * (x Wup). */
+int b200_gemm_w4a16_ex(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
+                       int groupsize, int layout, int act, void* workspace, void* stream);
 
 /* ---- paged KV block allocator (host) + per-step bookkeeping (device) -------------------------------------
  * replaces fms-extras PagedKVCacheManager block bookkeeping (models/paged_causal_lm.py:338-353,
@@ -148,7 +158,7 @@ typedef struct {
   const void* bias;    /* fp16 [N] or NULL */
   int64_t N, K;
   int32_t groupsize;
-  int32_t _pad;
+  int32_t layout; /* B200_W4_LAYOUT_* of `qweight` */
 } B200Linear;
 
 typedef struct {

@@ -120,6 +120,32 @@ def test_gemm_w4a16(ops, T, N, K, gs):
     _close(got, ref, what=f"gemm_w4a16 {T}x{N}x{K} g{gs}")
 
 
+@pytest.mark.parametrize("T,I,K", [(64, 1024, 512), (5, 256, 256), (64, 11008, 4096)])
+def test_gemm_w4a16_gate_up_layout_and_fused_silu(ops, T, I, K):
+    """gate|up record order: the plain product is unchanged (up to the fp32 summation grouping of a different stream-K
+    split), and the fused epilogue equals linear -> b200_silu_mul bit for bit (same arithmetic,
+    flash_llama_modeling.py:332-335) and the oracle's SiLU * up."""
+    g = torch.Generator().manual_seed(T + I + K)
+    N, gs = 2 * I, 128
+    w = torch.randn(N, K, generator=g) * 0.05
+    qweight, qzeros, scales, _ = ogptq.quantize_rtn(w, gs)
+    x = torch.randn(T, K, generator=g).half()
+    qw, qz, sc, xd = qweight.to(DEV), qzeros.to(DEV), scales.to(DEV), x.to(DEV)
+    plain = ops.gemm_w4a16(xd, ops.gptq_pack(qw, qz, sc, gs), N, gs)
+    paired = ops.gptq_pack(qw, qz, sc, gs, layout=ops.W4_LAYOUT_GATE_UP)
+    same = ops.gemm_w4a16(xd, paired, N, gs, layout=ops.W4_LAYOUT_GATE_UP)
+    _close(same, plain.cpu(), what="gate|up layout vs plain layout")
+    assert (same != plain).float().mean().item() < 0.05  # only fp16 rounding flips from the regrouped fp32 sums
+    fused = ops.gemm_w4a16(xd, paired, N, gs, layout=ops.W4_LAYOUT_GATE_UP, silu_mul=True)
+    unfused = ops.silu_mul(same)
+    torch.cuda.synchronize()
+    assert fused.shape == (T, I)
+    assert torch.equal(fused, unfused), f"{(fused != unfused).sum().item()} elements differ"
+    ref = ogptq.gemm_half_q_half(x, qweight, qzeros, scales, None, gs).float()
+    ref = (torch.nn.functional.silu(ref[:, :I].half().float()).half() * ref[:, I:].half()).half()
+    _close(fused, ref, what=f"fused silu*up {T}x{I}x{K}")
+
+
 def test_gemm_w4a16_dequant_bit_exact(ops):
     """x = one-hot rows -> y[t] is row k_t of the dequantised matrix: must equal the oracle's fp16 W bit for bit."""
     g = torch.Generator().manual_seed(77)

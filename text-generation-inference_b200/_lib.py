@@ -35,14 +35,16 @@ SIGNATURES = {
     "b200_gemm_f16": (_I, [_P, _P, _P, _P, _L, _L, _L, _P, _P]),
     "b200_gptq_packed_bytes": (_L, [_L, _L, _I]),
     "b200_gptq_pack": (_I, [_P, _P, _P, _P, _L, _L, _I, _P]),
+    "b200_gptq_pack_ex": (_I, [_P, _P, _P, _P, _L, _L, _I, _I, _P]),
     "b200_gemm_w4a16": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _P, _P]),
+    "b200_gemm_w4a16_ex": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _P, _P]),
 }
 
 
 
 class B200Linear(ctypes.Structure):
     _fields_ = [("weight", _P), ("qweight", _P), ("qzeros", _P), ("scales", _P), ("bias", _P), ("N", _L), ("K", _L),
-                ("groupsize", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+                ("groupsize", ctypes.c_int32), ("layout", ctypes.c_int32)]
 
 
 class B200LlamaLayer(ctypes.Structure):

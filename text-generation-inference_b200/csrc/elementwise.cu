@@ -182,43 +182,51 @@ __global__ void embedding_kernel(const __half* __restrict__ table, const int64_t
 // ------------------------------------------------------------------------------------------------
 // greedy arg-max over fp16 logits (first index wins ties, like torch.argmax on a row scan)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) argmax_kernel(const __half* __restrict__ logits, int64_t* __restrict__ out, int64_t V,
-                                                       int64_t ld, const int64_t* __restrict__ banned) {
+constexpr int kArgmaxThreads = 1024;
+__global__ void __launch_bounds__(kArgmaxThreads) argmax_kernel(const __half* __restrict__ logits, int64_t* __restrict__ out, int64_t V,
+                                                                 int64_t ld, const int64_t* __restrict__ banned) {
   pdl_launch_dependents();
   pdl_wait();
   const __half* row = logits + (size_t)blockIdx.x * ld;
   // banned[row] >= 0: that token's score counts as -inf (min_new_tokens EOS mask, utils/tokens.py:244-246)
-  const int64_t ban = banned ? banned[blockIdx.x] : -1;
+  const int ban = banned ? (int)banned[blockIdx.x] : -1;
   float best = -INFINITY;
-  int64_t best_i = 0x7fffffffffffffffLL;
-  const int64_t V8 = V & ~7LL;
-  for (int64_t i = (int64_t)threadIdx.x * 8; i < V8; i += 256 * 8) {
-    uint4 v = *reinterpret_cast<const uint4*>(row + i);
+  int best_i = 0x7fffffff;
+  const int V8 = (int)(V & ~7LL);
+  // a thread visits its indices in increasing order, so a strict '>' keeps the first maximum
+  for (int i = threadIdx.x * 8; i < V8; i += kArgmaxThreads * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(row + i);
     const __half* hv = reinterpret_cast<const __half*>(&v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float f = (i + j == ban) ? -INFINITY : __half2float(hv[j]);
-      if (f > best || (f == best && i + j < best_i)) { best = f; best_i = i + j; }
+      const float f = (i + j == ban) ? -INFINITY : __half2float(hv[j]);
+      if (f > best) { best = f; best_i = i + j; }
     }
   }
-  for (int64_t i = V8 + threadIdx.x; i < V; i += 256) {
-    float f = (i == ban) ? -INFINITY : __half2float(row[i]);
+  for (int i = V8 + threadIdx.x; i < (int)V; i += kArgmaxThreads) {
+    const float f = (i == ban) ? -INFINITY : __half2float(row[i]);
     if (f > best || (f == best && i < best_i)) { best = f; best_i = i; }
   }
-  __shared__ float sv[8];
-  __shared__ int64_t si[8];
+  __shared__ float sv[kArgmaxThreads / 32];
+  __shared__ int si[kArgmaxThreads / 32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    int64_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
     if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
   }
   if (lane_id() == 0) { sv[warp_id()] = best; si[warp_id()] = best_i; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w)
-      if (sv[w] > best || (sv[w] == best && si[w] < best_i)) { best = sv[w]; best_i = si[w]; }
-    out[blockIdx.x] = best_i == 0x7fffffffffffffffLL ? 0 : best_i;
+  if (warp_id() == 0) {
+    best = sv[lane_id()];
+    best_i = si[lane_id()];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane_id() == 0) out[blockIdx.x] = best_i == 0x7fffffff ? 0 : best_i;
   }
 }
 
@@ -287,7 +295,7 @@ extern "C" int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int6
                            void* stream) {
   if (B == 0) return B200_OK;
   if (ld % 8 != 0) { b200_set_last_error("argmax: row stride must be a multiple of 8 halves"); return B200_ERR_ARG; }
-  B200_LAUNCH(argmax_kernel, dim3((unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const __half*)logits, out_ids, V, ld, banned_ids);
+  B200_LAUNCH(argmax_kernel, dim3((unsigned)B), dim3(kArgmaxThreads), 0, (cudaStream_t)stream, (const __half*)logits, out_ids, V, ld, banned_ids);
   b200_count_launches(1);
   return B200_OK;
 }

@@ -168,6 +168,14 @@ __device__ __forceinline__ void dequant_consts(uint32_t rec, uint32_t& scale2, u
   nz64 = 0xD400D400u + (z2 << 4);              // -(64 + zero), exact
 }
 
+// fp16(fp16(silu(fp16 g)) * fp16 u) from the two fp32 accumulators: exactly what the separate linear (fp16 output) followed
+// by silu_mul_kernel (elementwise.cu; torch fp16 SiLU = fp32 x / (1 + exp(-x)), one rounding, then an fp16 multiply) gives
+__device__ __forceinline__ __half silu_mul_f16(float gate_acc, float up_acc) {
+  const float g = __half2float(__float2half_rn(gate_acc));
+  const __half a = __float2half_rn(g / (1.f + expf(-g)));
+  return __hmul(a, __float2half_rn(up_acc));
+}
+
 struct W4Params {
   __half* y;
   float* partial;   // [token tile][super-tile][contributor][kW4R][TN][128] fp32
@@ -181,6 +189,9 @@ struct W4Params {
   int total_su;     // per token tile
   int max_contrib;  // partial slots per super-tile
   int rec_bytes;    // 8192 + group_rows * 512
+  int half_tiles;   // 0: super-tile s = feature tiles (2s, 2s+1); > 0 ("gate|up" layout): tiles (s, s + half_tiles)
+  int act;          // 1: y[t, 128 s + m] = fp16(silu(fp16 gate)) * fp16 up  (needs the gate|up layout), row stride ldy
+  int ldy;          // output row stride in halves
   unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
 };
 
@@ -438,31 +449,49 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
       mbar_wait_relaxed(&tmem_full[buf], C::kDBufs == 2 ? ((seg >> 1) & 1) : (seg & 1));
       tcgen05_fence_after();
       W4_TRACE(8 + (seg & 3) * 2, 0);
-#pragma unroll 1
-      for (int r = 0; r < kW4R; ++r) {
-        const int n = (sup * kW4R + r) * kW4TileM + m;
-        const bool n_ok = n < p.N;
-        const float bv = (p.bias && n_ok && n_contrib == 1) ? __half2float(p.bias[n]) : 0.f;
-        constexpr int kCh = TN < 64 ? TN : 64;  // columns fetched per tcgen05.wait::ld
+      {
+        // both tiles of the super-tile, kCh token columns at a time
+        const int n0 = (p.half_tiles ? sup : sup * kW4R) * kW4TileM + m;
+        const int n1 = (p.half_tiles ? sup + p.half_tiles : sup * kW4R + 1) * kW4TileM + m;
+        const bool ok0 = n0 < p.N, ok1 = n1 < p.N;
+        const bool direct = n_contrib == 1;
+        const float bv0 = (p.bias && ok0 && direct) ? __half2float(p.bias[n0]) : 0.f;
+        const float bv1 = (p.bias && ok1 && direct) ? __half2float(p.bias[n1]) : 0.f;
+        constexpr int kCh = TN < 32 ? TN : 32;  // columns fetched per tcgen05.wait::ld
 #pragma unroll 1
         for (int c = 0; c < TN; c += kCh) {
-          uint32_t d[kCh];
+          uint32_t d0[kCh], d1[kCh];
 #pragma unroll
-          for (int q = 0; q < kCh / 16; ++q)
-            tmem_ld_32x32b_x16(tmem_d + lane_base + (buf * kW4R + r) * TN + c + q * 16, reinterpret_cast<uint32_t(&)[16]>(d[q * 16]));
+          for (int q = 0; q < kCh / 16; ++q) {
+            tmem_ld_32x32b_x16(tmem_d + lane_base + (buf * kW4R + 0) * TN + c + q * 16, reinterpret_cast<uint32_t(&)[16]>(d0[q * 16]));
+            tmem_ld_32x32b_x16(tmem_d + lane_base + (buf * kW4R + 1) * TN + c + q * 16, reinterpret_cast<uint32_t(&)[16]>(d1[q * 16]));
+          }
           tmem_ld_wait();
-          if (n_contrib == 1) {
-            if (n_ok) {
+          if (!direct) {
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) {
+              if (t0 + c + j < p.T) {
+                part[(c + j) * kW4TileM + m] = __uint_as_float(d0[j]);
+                part[(TN + c + j) * kW4TileM + m] = __uint_as_float(d1[j]);
+              }
+            }
+          } else if (p.act) {
+            if (ok0) {
 #pragma unroll
               for (int j = 0; j < kCh; ++j) {
                 const int t = t0 + c + j;
-                if (t < p.T) p.y[(size_t)t * p.N + n] = __float2half_rn(__uint_as_float(d[j]) + bv);
+                if (t < p.T) p.y[(size_t)t * p.ldy + n0] = silu_mul_f16(__uint_as_float(d0[j]) + bv0, __uint_as_float(d1[j]) + bv1);
               }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < kCh; ++j)
-              if (t0 + c + j < p.T) part[(r * TN + c + j) * kW4TileM + m] = __uint_as_float(d[j]);
+            for (int j = 0; j < kCh; ++j) {
+              const int t = t0 + c + j;
+              if (t < p.T) {
+                if (ok0) p.y[(size_t)t * p.ldy + n0] = __float2half_rn(__uint_as_float(d0[j]) + bv0);
+                if (ok1) p.y[(size_t)t * p.ldy + n1] = __float2half_rn(__uint_as_float(d1[j]) + bv1);
+              }
+            }
           }
         }
       }
@@ -512,31 +541,67 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
     const int n_vec = kW4R * rows * (kW4TileM / 4);  // float4 elements: [r][row][32]
     const int per = (n_vec + n_contrib - 1) / n_contrib;
     const int hi = min(n_vec, (my_contrib + 1) * per);
-    for (int idx = my_contrib * per + (int)threadIdx.x; idx < hi; idx += kW4Threads) {
-      const int r = idx / (rows * (kW4TileM / 4));
-      const int rem = idx - r * rows * (kW4TileM / 4);
-      const int tt = rem / (kW4TileM / 4), mm = (rem % (kW4TileM / 4)) * 4;
-      const size_t off = (size_t)(r * TN + tt) * kW4TileM + mm;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c0 = 0; c0 < n_contrib; c0 += 4) {  // contributor order: deterministic
-        float4 ld[4];
+    constexpr size_t kPartStride = (size_t)kW4R * TN * kW4TileM;
+    if (!p.act) {
+      for (int idx = my_contrib * per + (int)threadIdx.x; idx < hi; idx += kW4Threads) {
+        const int r = idx / (rows * (kW4TileM / 4));
+        const int rem = idx - r * rows * (kW4TileM / 4);
+        const int tt = rem / (kW4TileM / 4), mm = (rem % (kW4TileM / 4)) * 4;
+        const size_t off = (size_t)(r * TN + tt) * kW4TileM + mm;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c0 = 0; c0 < n_contrib; c0 += 4) {  // contributor order: deterministic
+          float4 ld[4];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          ld[cc] = (c0 + cc < n_contrib) ? __ldcg(reinterpret_cast<const float4*>(&base[(size_t)(c0 + cc) * (kW4R * TN * kW4TileM) + off]))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int cc = 0; cc < 4; ++cc)
+            ld[cc] = (c0 + cc < n_contrib) ? __ldcg(reinterpret_cast<const float4*>(&base[(size_t)(c0 + cc) * kPartStride + off]))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) { acc.x += ld[cc].x; acc.y += ld[cc].y; acc.z += ld[cc].z; acc.w += ld[cc].w; }
-      }
-      const int nn = (sup * kW4R + r) * kW4TileM + mm;
-      if (nn < p.N) {  // N % 32 == 0: a float4 never straddles N
-        if (p.bias) {
-          acc.x += __half2float(p.bias[nn]); acc.y += __half2float(p.bias[nn + 1]);
-          acc.z += __half2float(p.bias[nn + 2]); acc.w += __half2float(p.bias[nn + 3]);
+          for (int cc = 0; cc < 4; ++cc) { acc.x += ld[cc].x; acc.y += ld[cc].y; acc.z += ld[cc].z; acc.w += ld[cc].w; }
         }
-        uint2 o;
-        o.x = pack_half2(acc.x, acc.y);
-        o.y = pack_half2(acc.z, acc.w);
-        *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.N + nn]) = o;
+        const int nn = (p.half_tiles ? sup + r * p.half_tiles : sup * kW4R + r) * kW4TileM + mm;
+        if (nn < p.N) {  // N % 32 == 0: a float4 never straddles N
+          if (p.bias) {
+            acc.x += __half2float(p.bias[nn]); acc.y += __half2float(p.bias[nn + 1]);
+            acc.z += __half2float(p.bias[nn + 2]); acc.w += __half2float(p.bias[nn + 3]);
+          }
+          uint2 o;
+          o.x = pack_half2(acc.x, acc.y);
+          o.y = pack_half2(acc.z, acc.w);
+          *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.ldy + nn]) = o;
+        }
+      }
+    } else {
+      // fused SiLU(gate) * up: an element needs both tiles of the super-tile; slices over [row][32 float4]
+      const int n_vec_a = rows * (kW4TileM / 4);
+      const int per_a = (n_vec_a + n_contrib - 1) / n_contrib;
+      const int hi_a = min(n_vec_a, (my_contrib + 1) * per_a);
+      for (int idx = my_contrib * per_a + (int)threadIdx.x; idx < hi_a; idx += kW4Threads) {
+        const int tt = idx / (kW4TileM / 4), mm = (idx % (kW4TileM / 4)) * 4;
+        const size_t off = (size_t)tt * kW4TileM + mm;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c0 = 0; c0 < n_contrib; c0 += 2) {  // contributor order: deterministic
+          float4 lg[2], lu[2];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const bool in = c0 + cc < n_contrib;
+            lg[cc] = in ? __ldcg(reinterpret_cast<const float4*>(&base[(size_t)(c0 + cc) * kPartStride + off])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            lu[cc] = in ? __ldcg(reinterpret_cast<const float4*>(&base[(size_t)(c0 + cc) * kPartStride + (size_t)TN * kW4TileM + off]))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            g.x += lg[cc].x; g.y += lg[cc].y; g.z += lg[cc].z; g.w += lg[cc].w;
+            u.x += lu[cc].x; u.y += lu[cc].y; u.z += lu[cc].z; u.w += lu[cc].w;
+          }
+        }
+        const int nn = sup * kW4TileM + mm;  // column of the [T, N / 2] output
+        const int ng = nn, nu = nn + p.half_tiles * kW4TileM;
+        if (p.bias) {
+          g.x += __half2float(p.bias[ng]); g.y += __half2float(p.bias[ng + 1]); g.z += __half2float(p.bias[ng + 2]); g.w += __half2float(p.bias[ng + 3]);
+          u.x += __half2float(p.bias[nu]); u.y += __half2float(p.bias[nu + 1]); u.z += __half2float(p.bias[nu + 2]); u.w += __half2float(p.bias[nu + 3]);
+        }
+        __half o[4] = {silu_mul_f16(g.x, u.x), silu_mul_f16(g.y, u.y), silu_mul_f16(g.z, u.z), silu_mul_f16(g.w, u.w)};
+        *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.ldy + nn]) = *reinterpret_cast<uint2*>(o);
       }
     }
     W4_TRACE(42 + f * 3, 0);
@@ -558,7 +623,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
 // checkpoint tensors -> unit records.  One thread per output u32.
 __global__ void gptq_pack_kernel(const uint32_t* __restrict__ qweight, const uint32_t* __restrict__ qzeros,
                                  const __half* __restrict__ scales, uint32_t* __restrict__ packed, int64_t K, int64_t N, int groupsize,
-                                 int group_rows, int nkb, int64_t n_words_total) {
+                                 int group_rows, int nkb, int64_t n_words_total, int half_tiles) {
   const int rec_words = (kW4WordBytes + group_rows * kW4MetaRowBytes) / 4;
   const int64_t G = (K + groupsize - 1) / groupsize;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_words_total; o += (int64_t)gridDim.x * blockDim.x) {
@@ -566,7 +631,7 @@ __global__ void gptq_pack_kernel(const uint32_t* __restrict__ qweight, const uin
     const int r = (int)(o - rec * rec_words);
     const int64_t sup = rec / ((int64_t)nkb * kW4R);
     const int kb = (int)((rec / kW4R) % nkb);
-    const int64_t tile = sup * kW4R + rec % kW4R;
+    const int64_t tile = half_tiles ? sup + (rec % kW4R) * half_tiles : sup * kW4R + rec % kW4R;
     uint32_t out = 0;
     if (r < kW4WordBytes / 4) {
       const int c = r / (kW4TileM * 4), m = (r / 4) % kW4TileM, j = r % 4;
@@ -662,12 +727,26 @@ extern "C" int64_t b200_gptq_packed_bytes(int64_t K, int64_t N, int groupsize) {
   return ns * kW4R * nkb * (kW4WordBytes + gr * kW4MetaRowBytes);  // the last super-tile is padded with empty tiles
 }
 
+// layout 0: super-tile s = feature tiles (2s, 2s+1).  layout 1 ("gate|up", for a fused [gate; up] projection with
+// N = 2 I, I % 128 == 0): super-tile s = tiles (s, s + I/128), i.e. gate feature n sits next to up feature n, which is what
+// lets the GEMM apply SiLU(gate) * up in its epilogue (b200_gemm_w4a16_ex act = 1).
+static int w4_half_tiles(int64_t N, int layout, const char* who) {
+  if (layout == 0) return 0;
+  if (layout != 1 || N % (2 * kW4TileM) != 0) {
+    b200_set_last_error((std::string(who) + ": the gate|up layout needs N % 256 == 0").c_str());
+    return -1;
+  }
+  return (int)(N / (2 * kW4TileM));
+}
+
 // qweight int32 [K/8, N], qzeros int32 [ceil(K/g), N/8], scales fp16 [ceil(K/g), N] (checkpoint layout, left untouched)
 // -> packed (b200_gptq_packed_bytes bytes, 16-byte aligned).  Groups are k // groupsize (trivial g_idx).
-extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
-                              int groupsize, void* stream) {
+extern "C" int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
+                                 int groupsize, int layout, void* stream) {
   if (!w4_check_shape(N, K, groupsize, "gptq_pack")) return B200_ERR_ARG;
   if (((uintptr_t)packed & 15) != 0) { b200_set_last_error("gptq_pack: packed buffer must be 16-byte aligned"); return B200_ERR_ARG; }
+  const int half_tiles = w4_half_tiles(N, layout, "gptq_pack");
+  if (half_tiles < 0) return B200_ERR_ARG;
   const int gr = w4_group_rows(K, &groupsize);
   const int nkb = (int)((K + kW4BlockK - 1) / kW4BlockK);
   const int64_t n_words = b200_gptq_packed_bytes(K, N, groupsize) / 4;
@@ -675,10 +754,14 @@ extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const voi
   if (blocks > 148 * 16) blocks = 148 * 16;
   gptq_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qweight, (const uint32_t*)qzeros,
                                                                         (const __half*)scales, (uint32_t*)packed, K, N, groupsize, gr,
-                                                                        nkb, n_words);
+                                                                        nkb, n_words, half_tiles);
   B200_CHECK_LAUNCH();
   b200_count_launches(1);
   return B200_OK;
+}
+extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
+                              int groupsize, void* stream) {
+  return b200_gptq_pack_ex(qweight, qzeros, scales, packed, K, N, groupsize, 0, stream);
 }
 
 // bytes of split-K partials the int4 GEMM may write for this shape (the tile counters sit in the first 64 KiB)
@@ -690,7 +773,7 @@ int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K) {
 
 template <int TN, int kGR>
 static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, void* workspace, const void* bias, int T, int N,
-                          const W4Plan& pl, cudaStream_t st) {
+                          const W4Plan& pl, int half_tiles, int act, cudaStream_t st) {
   using C = GemmW4Cfg<TN>;
   static bool configured = false;
   if (!configured) {
@@ -712,6 +795,9 @@ static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, vo
   p.total_su = pl.n_super * pl.nkb;
   p.max_contrib = pl.max_contrib;
   p.rec_bytes = kW4WordBytes + kGR * kW4MetaRowBytes;
+  p.half_tiles = half_tiles;
+  p.act = act;
+  p.ldy = act ? N / 2 : N;
   p.trace = g_w4_trace;
   dim3 grid(pl.n_ctas, pl.n_tiles_t, 1);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 0, st);
@@ -721,12 +807,17 @@ static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, vo
   return B200_OK;
 }
 
-// packed: output of b200_gptq_pack for the same (K, N, groupsize).
-// workspace as for b200_gemm_f16 (b200_gemm_workspace_bytes); without it every CTA takes whole tiles (no stream-K).
-extern "C" int b200_gemm_w4a16(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
-                               int groupsize, void* workspace, void* stream) {
+// packed: output of b200_gptq_pack[_ex] for the same (K, N, groupsize, layout).
+// act = 1 (layout 1 only): y [T, N/2] = SiLU(x Wgate) * (x Wup), the LlamaMLP activation (flash_llama_modeling.py:332-335) fused
+// into the projection.  workspace as for b200_gemm_f16 (b200_gemm_workspace_bytes); without it every CTA takes whole
+// super-tiles (no stream-K).
+extern "C" int b200_gemm_w4a16_ex(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
+                                  int groupsize, int layout, int act, void* workspace, void* stream) {
   if (T == 0 || N == 0) return B200_OK;
   if (!w4_check_shape(N, K, groupsize, "gemm_w4a16")) return B200_ERR_ARG;
+  const int half_tiles = w4_half_tiles(N, layout, "gemm_w4a16");
+  if (half_tiles < 0) return B200_ERR_ARG;
+  if (act != 0 && (act != 1 || layout != 1)) { b200_set_last_error("gemm_w4a16: act = 1 needs the gate|up layout"); return B200_ERR_ARG; }
   const int gr = w4_group_rows(K, &groupsize);
   W4Plan pl = plan_w4(T, N, K, num_sms());
   if (pl.max_contrib > 1 && (!workspace || (int64_t)pl.n_super * pl.n_tiles_t * 8 > kW4CounterBytes || pl.n_ctas > num_sms())) {
@@ -737,10 +828,10 @@ extern "C" int b200_gemm_w4a16(const void* x, const void* packed, const void* bi
   const CUtensorMap* mx = get_tmap_2d(x, T, K, K, pl.TN, 64, TmapDtype::kF16, TmapSwizzle::k128B);
   if (!mx) return B200_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-#define W4_DISPATCH(TNV)                                                                                          \
-  (gr == 1 ? launch_gemm_w4<TNV, 1>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, st)                       \
-           : gr == 2 ? launch_gemm_w4<TNV, 2>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, st)             \
-                     : launch_gemm_w4<TNV, 4>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, st))
+#define W4_DISPATCH(TNV)                                                                                                    \
+  (gr == 1 ? launch_gemm_w4<TNV, 1>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, st)                \
+           : gr == 2 ? launch_gemm_w4<TNV, 2>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, st)      \
+                     : launch_gemm_w4<TNV, 4>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, st))
   switch (pl.TN) {
     case 16: return W4_DISPATCH(16);
     case 32: return W4_DISPATCH(32);
@@ -748,4 +839,8 @@ extern "C" int b200_gemm_w4a16(const void* x, const void* packed, const void* bi
     default: return W4_DISPATCH(128);
   }
 #undef W4_DISPATCH
+}
+extern "C" int b200_gemm_w4a16(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
+                               int groupsize, void* workspace, void* stream) {
+  return b200_gemm_w4a16_ex(x, packed, bias, y, T, N, K, groupsize, 0, 0, workspace, stream);
 }

@@ -9,7 +9,7 @@
 
 static int linear(const B200Linear* L, const void* x, void* y, int64_t T, void* gemm_ws, void* stream) {
   if (L->qweight)
-    return b200_gemm_w4a16(x, L->qweight, L->bias, y, T, L->N, L->K, L->groupsize, gemm_ws, stream);
+    return b200_gemm_w4a16_ex(x, L->qweight, L->bias, y, T, L->N, L->K, L->groupsize, L->layout, 0, gemm_ws, stream);
   return b200_gemm_f16(x, L->weight, L->bias, y, T, L->N, L->K, gemm_ws, stream);
 }
 
@@ -64,8 +64,14 @@ extern "C" int b200_llama_mlp_block(const B200LlamaWeights* w, const B200LlamaSt
   const int64_t T = s->T;
   const B200LlamaLayer* L = &w->layers[layer];
   RUN(b200_rmsnorm_residual(s->hidden, s->residual, L->post_ln, s->normed, s->residual, T, w->hidden_size, w->rms_eps, stream));
-  RUN(linear(&L->gate_up, s->normed, s->gate_up, T, s->gemm_ws, stream));
-  RUN(b200_silu_mul(s->gate_up, s->act, T, L->gate_up.N / 2, stream));
+  if (L->gate_up.qweight && L->gate_up.layout == B200_W4_LAYOUT_GATE_UP) {
+    // int4 gate|up layout: SiLU(gate) * up is the GEMM's epilogue, the [T, 2 I] intermediate never exists
+    RUN(b200_gemm_w4a16_ex(s->normed, L->gate_up.qweight, L->gate_up.bias, s->act, T, L->gate_up.N, L->gate_up.K, L->gate_up.groupsize,
+                           B200_W4_LAYOUT_GATE_UP, 1, s->gemm_ws, stream));
+  } else {
+    RUN(linear(&L->gate_up, s->normed, s->gate_up, T, s->gemm_ws, stream));
+    RUN(b200_silu_mul(s->gate_up, s->act, T, L->gate_up.N / 2, stream));
+  }
   RUN(linear(&L->down, s->act, s->hidden, T, s->gemm_ws, stream));
   return B200_OK;
 }

@@ -118,12 +118,14 @@ class FlashLlamaModel(nn.Module):
         self.num_key_value_heads = self.layers[0].self_attn.num_key_value_heads
 
 
-def _fill_linear(dst: _lib.B200Linear, lin) -> None:
+def _fill_linear(dst: _lib.B200Linear, lin, gate_up: bool = False) -> None:
+    dst.layout = 0
     if isinstance(lin, Ex4bitLinearV2):
-        lin.post_init()
+        lin.post_init(layout=1 if gate_up else 0)  # gate|up record order: SiLU * up fuses into the GEMM epilogue
         dst.weight = None
         dst.qweight, dst.qzeros, dst.scales = lin.q_handle.data_ptr(), None, None
         dst.N, dst.K, dst.groupsize = lin.outfeatures, lin.infeatures, lin.group_size
+        dst.layout = lin.pack_layout
     elif isinstance(lin, FastLinear):
         dst.weight = lin.weight.data_ptr()
         dst.qweight = dst.qzeros = dst.scales = None
@@ -214,7 +216,7 @@ class FlashLlamaForCausalLM(nn.Module):
             for name, lin in (("qkv", layer.self_attn.query_key_value.linear), ("o", layer.self_attn.o_proj.linear),
                               ("gate_up", layer.mlp.gate_up_proj.linear), ("down", layer.mlp.down_proj.linear)):
                 dst = getattr(arr[i], name)
-                _fill_linear(dst, lin)
+                _fill_linear(dst, lin, gate_up=(name == "gate_up"))
                 shapes.append((dst.N, dst.K))
         head = self.lm_head.linear
         assert isinstance(head, FastLinear), "GPTQ never quantizes the head (utils/layers.py:236-237)"

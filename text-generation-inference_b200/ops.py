@@ -154,8 +154,13 @@ def gemm_f16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
     return out
 
 
-def gptq_pack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, groupsize: int) -> torch.Tensor:
-    """Checkpoint GPTQ tensors of one linear -> the kernel's unit-record stream (uint8 tensor)."""
+W4_LAYOUT_PLAIN, W4_LAYOUT_GATE_UP = 0, 1
+
+
+def gptq_pack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, groupsize: int,
+              layout: int = W4_LAYOUT_PLAIN) -> torch.Tensor:
+    """Checkpoint GPTQ tensors of one linear -> the kernel's unit-record stream (uint8 tensor).
+    layout = W4_LAYOUT_GATE_UP pairs gate tile s with up tile s (fused [gate; up] projection, N = 2 I, I % 128 == 0)."""
     _req(qweight, torch.int32, "qweight")
     _req(qzeros, torch.int32, "qzeros")
     _req(scales, torch.float16, "scales")
@@ -167,23 +172,26 @@ def gptq_pack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
     if nbytes < 0:
         raise _lib.B200Error(f"gptq_pack: {lib.b200_last_error().decode()}")
     packed = torch.empty(nbytes, dtype=torch.uint8, device=qweight.device)
-    _lib.check(lib.b200_gptq_pack(_ptr(qweight), _ptr(qzeros), _ptr(scales), _ptr(packed), K, N, groupsize, _stream()), "gptq_pack")
+    _lib.check(lib.b200_gptq_pack_ex(_ptr(qweight), _ptr(qzeros), _ptr(scales), _ptr(packed), K, N, groupsize, layout, _stream()),
+               "gptq_pack")
     return packed
 
 
 def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, N: int, groupsize: int, bias: Optional[torch.Tensor] = None,
-               out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [T,K] fp16 @ dequant(packed) -> [T,N] fp16; `packed` from gptq_pack for the same (K, N, groupsize)."""
+               out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None, layout: int = W4_LAYOUT_PLAIN,
+               silu_mul: bool = False) -> torch.Tensor:
+    """x [T,K] fp16 @ dequant(packed) -> [T,N] fp16; `packed` from gptq_pack for the same (K, N, groupsize, layout).
+    silu_mul (gate|up layout only): returns [T, N/2] = SiLU(x Wgate) * (x Wup)."""
     _req(x, torch.float16, "x")
     _req(packed, torch.uint8, "packed")
     assert x.is_contiguous() and packed.is_contiguous()
     T, K = x.shape
     if out is None:
-        out = torch.empty(T, N, dtype=torch.float16, device=x.device)
+        out = torch.empty(T, N // 2 if silu_mul else N, dtype=torch.float16, device=x.device)
     if workspace is None:
         workspace = gemm_workspace(x.device, T, N, K)
-    _lib.check(_lib.load().b200_gemm_w4a16(_ptr(x), _ptr(packed), _ptr(bias), _ptr(out), T, N, K, groupsize, _ptr(workspace),
-                                           _stream()), "gemm_w4a16")
+    _lib.check(_lib.load().b200_gemm_w4a16_ex(_ptr(x), _ptr(packed), _ptr(bias), _ptr(out), T, N, K, groupsize, layout,
+                                              int(silu_mul), _ptr(workspace), _stream()), "gemm_w4a16")
     return out
 
 

@@ -21,6 +21,7 @@ class Ex4bitLinearV2(nn.Module):
         super().__init__()
         assert bits == 4, "b200 GPTQ kernel supports 4-bit only"  # exllamav2.py:105
         self.q_handle = None
+        self.pack_layout = 0  # ops.W4_LAYOUT_*: how q_handle's unit records are ordered
         self.qweight = qweight
         self.qzeros = qzeros
         self.scales = scales.to(torch.float16)
@@ -37,13 +38,18 @@ class Ex4bitLinearV2(nn.Module):
             if not trivial and not bool((g_idx == 0).all()):
                 raise NotImplementedError("act-order (non-trivial g_idx) checkpoints are not supported yet")
 
-    def post_init(self, temp_dq=None):
+    def post_init(self, temp_dq=None, layout: int = 0):
         """exllamav2.py:124-137 (make_q_matrix): one-time conversion to the kernel layout; the checkpoint tensors are
-        released afterwards (the packed buffer holds everything the GEMM reads)."""
+        released afterwards (the packed buffer holds everything the GEMM reads).  `layout` = ops.W4_LAYOUT_GATE_UP for
+        a fused [gate; up] projection (lets the step runtime fuse SiLU * up into the GEMM); results of forward() are
+        the same either way."""
         if self.q_handle is None:
             assert self.qweight.device.type == "cuda"
+            if layout == 1 and self.outfeatures % 256 != 0:
+                layout = 0
             self.q_handle = _ops().gptq_pack(self.qweight.contiguous(), self.qzeros.contiguous(), self.scales.contiguous(),
-                                             self.group_size)
+                                             self.group_size, layout)
+            self.pack_layout = layout
             self.qweight = self.qzeros = self.scales = None
 
     def forward(self, x, force_cuda=False):
@@ -51,7 +57,7 @@ class Ex4bitLinearV2(nn.Module):
             self.post_init()
         out_shape = x.shape[:-1] + (self.outfeatures,)
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        out = _ops().gemm_w4a16(x2, self.q_handle, self.outfeatures, self.group_size, self.bias)
+        out = _ops().gemm_w4a16(x2, self.q_handle, self.outfeatures, self.group_size, self.bias, layout=self.pack_layout)
         return out.view(out_shape)
 
     def temp_dq_size(self):
