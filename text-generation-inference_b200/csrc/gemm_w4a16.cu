@@ -36,6 +36,7 @@
 #include "common.cuh"
 #include "tmap.cuh"
 
+#include <cstdlib>
 #include <string>
 
 namespace b200 {
@@ -670,14 +671,28 @@ static int num_sms() {
   return n;
 }
 
+// k-blocks per tile.  Rounded up to a multiple of 8 (empty records; the activation TMA zero-fills past K) when that adds
+// at most 5 % of traffic: it lets a super-tile be cut into 2 / 4 / 8 equal CTA shares (Llama-2 down_proj: 86 -> 88).
+static int w4_nkb(int64_t K) {
+  const int nkb = (int)((K + kW4BlockK - 1) / kW4BlockK);
+  const int up = (nkb + 7) / 8 * 8;
+  return (up - nkb) * 20 <= nkb ? up : nkb;
+}
+
 struct W4Plan {
   int TN, nkb, n_super, n_tiles_t, su_per_cta, n_ctas, max_contrib;
 };
 
+// Decode (one token tile): how many super-units per CTA.  Candidates are the balanced stream-K cut (every SM the same
+// number of units, but most CTAs then straddle two super-tiles: two fix-ups at the tail) and the aligned cuts nkb / d
+// (a CTA = 1/d of one super-tile: one fix-up with d contributors, or none for d = 1, at the price of idle SMs when
+// n_super * d is not close to a multiple of the SM count).  Costs in microseconds fitted to tools/sweep_w4_su.py on B200
+// (cold weights): 0.35 per unit in the main loop, ~1 for a direct epilogue, 4.5-6 for one split-K fix-up (partial store,
+// gpu-scope fence, waiting for the slowest contributor, L2-latency-bound slice reduction), ~10 when CTAs straddle.
 static W4Plan plan_w4(int64_t T, int64_t N, int64_t K, int sms) {
   W4Plan pl;
   pl.TN = T <= 16 ? 16 : T <= 32 ? 32 : T <= 64 ? 64 : 128;
-  pl.nkb = (int)((K + kW4BlockK - 1) / kW4BlockK);
+  pl.nkb = w4_nkb(K);
   pl.n_super = (int)((N + kW4R * kW4TileM - 1) / (kW4R * kW4TileM));
   pl.n_tiles_t = (int)((T + pl.TN - 1) / pl.TN);
   const int total = pl.n_super * pl.nkb;
@@ -685,8 +700,27 @@ static W4Plan plan_w4(int64_t T, int64_t N, int64_t K, int sms) {
     pl.su_per_cta = pl.nkb;  // whole super-tiles (prefill: plenty of tiles)
   } else {
     const int ctas = total < sms ? total : sms;
-    pl.su_per_cta = (total + ctas - 1) / ctas;
-    if (pl.su_per_cta < 2 && pl.nkb >= 2) pl.su_per_cta = 2;  // one unit per team at least
+    int best = (total + ctas - 1) / ctas;
+    if (best < 2 && pl.nkb >= 2) best = 2;  // one unit per team at least
+    auto cost = [&](int su, bool aligned, int d) {
+      const float fix = aligned ? (d == 1 ? 1.0f : 4.5f + 0.2f * d) : 10.0f;
+      return 0.35f * kW4R * su + fix;
+    };
+    float best_cost = cost(best, pl.nkb % best == 0, pl.nkb / best);
+    for (int d = 1; d <= 8; d *= 2) {
+      if (pl.nkb % d != 0) break;
+      const int su = pl.nkb / d;
+      if ((int64_t)pl.n_super * d > sms || su < 2) continue;
+      const float c = cost(su, true, d);
+      if (c < best_cost) { best_cost = c; best = su; }
+    }
+    pl.su_per_cta = best;
+    static int env_su = -1;  // experiments: B200_W4_SU forces the cut
+    if (env_su < 0) {
+      const char* e = getenv("B200_W4_SU");
+      env_su = e ? atoi(e) : 0;
+    }
+    if (env_su > 0 && (total + env_su - 1) / env_su <= sms) pl.su_per_cta = env_su;
   }
   pl.n_ctas = (total + pl.su_per_cta - 1) / pl.su_per_cta;
   pl.max_contrib = (pl.nkb + pl.su_per_cta - 1) / pl.su_per_cta + 1;
@@ -723,7 +757,7 @@ static bool w4_check_shape(int64_t N, int64_t K, int groupsize, const char* who)
 extern "C" int64_t b200_gptq_packed_bytes(int64_t K, int64_t N, int groupsize) {
   if (!w4_check_shape(N, K, groupsize, "gptq_packed_bytes")) return B200_ERR_ARG;
   const int gr = w4_group_rows(K, &groupsize);
-  const int64_t nkb = (K + kW4BlockK - 1) / kW4BlockK, ns = (N + kW4R * kW4TileM - 1) / (kW4R * kW4TileM);
+  const int64_t nkb = w4_nkb(K), ns = (N + kW4R * kW4TileM - 1) / (kW4R * kW4TileM);
   return ns * kW4R * nkb * (kW4WordBytes + gr * kW4MetaRowBytes);  // the last super-tile is padded with empty tiles
 }
 
@@ -748,7 +782,7 @@ extern "C" int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const 
   const int half_tiles = w4_half_tiles(N, layout, "gptq_pack");
   if (half_tiles < 0) return B200_ERR_ARG;
   const int gr = w4_group_rows(K, &groupsize);
-  const int nkb = (int)((K + kW4BlockK - 1) / kW4BlockK);
+  const int nkb = w4_nkb(K);
   const int64_t n_words = b200_gptq_packed_bytes(K, N, groupsize) / 4;
   int64_t blocks = (n_words + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -766,7 +800,7 @@ extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const voi
 
 // bytes of split-K partials the int4 GEMM may write for this shape (the tile counters sit in the first 64 KiB)
 int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K) {
-  const W4Plan pl = plan_w4(T, N, K, 148);
+  const W4Plan pl = plan_w4(T, N, K, num_sms());
   if (pl.max_contrib <= 1) return 0;
   return (int64_t)pl.n_tiles_t * pl.n_super * pl.max_contrib * kW4R * pl.TN * kW4TileM * 4;
 }
