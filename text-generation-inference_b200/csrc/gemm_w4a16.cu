@@ -239,12 +239,28 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
   } while (0)
   W4_TRACE(0, 0);
 
+  // The weight stream does not depend on anything: the W producer initialises its own barriers and issues the first ring
+  // of unit records before the CTA-wide set-up barrier (TMEM allocation, the other barriers), so HBM latency overlaps it.
+  int w_issued = 0;
+  if (warp == kW4WProdWarp) {
+    if (elect_one()) {
+      for (int s = 0; s < C::kWStages; ++s) {
+        mbar_init(&full_w[s], 1);
+        mbar_init(&empty_w[s], 4);  // the 4 warps of the team that owns the stage
+      }
+      mbar_fence_init();
+      const uint64_t pol_w = policy_evict_first();
+      const unsigned char* src = p.packed + (size_t)su0 * kW4R * p.rec_bytes;
+      const int n0 = min(n_units, C::kWStages);
+      for (int i = 0; i < n0; ++i) {
+        mbar_arrive_expect_tx(&full_w[i], p.rec_bytes);
+        tma_bulk_g2s_hint(w_ring + i * kW4RecMaxBytes, src + (size_t)i * p.rec_bytes, p.rec_bytes, &full_w[i], pol_w);
+      }
+    }
+    w_issued = min(n_units, C::kWStages);
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_x);
-    for (int s = 0; s < C::kWStages; ++s) {
-      mbar_init(&full_w[s], 1);
-      mbar_init(&empty_w[s], 4);  // the 4 warps of the team that owns the stage
-    }
     for (int s = 0; s < C::kXStages; ++s) mbar_init(&full_x[s], 1);
     for (int b = 0; b < C::kSuRing; ++b) mbar_init(&su_done[b], 1);
     for (int b = 0; b < 2; ++b) {
@@ -266,12 +282,13 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
   W4_TRACE(1, 0);
 
   if (warp == kW4WProdWarp) {
-    // ------------------------------------------------------------------ TMA producer: unit records (HBM stream)
+    // ------------------------------------------------------------------ TMA producer: unit records (HBM stream); the first
+    // ring was issued above
     if (elect_one()) {
       const uint64_t pol_w = policy_evict_first();
-      const unsigned char* src = p.packed + (size_t)su0 * kW4R * p.rec_bytes;
-      int s = 0, ph = 1;
-      for (int i = 0; i < n_units; ++i) {
+      const unsigned char* src = p.packed + ((size_t)su0 * kW4R + w_issued) * p.rec_bytes;
+      int s = 0, ph = 0;  // stage 0 again: wait for its first release
+      for (int i = w_issued; i < n_units; ++i) {
         mbar_wait(&empty_w[s], ph);
         mbar_arrive_expect_tx(&full_w[s], p.rec_bytes);
         tma_bulk_g2s_hint(w_ring + s * kW4RecMaxBytes, src, p.rec_bytes, &full_w[s], pol_w);
