@@ -120,8 +120,12 @@ int b200_gptq_pack(const void* qweight, const void* qzeros, const void* scales, 
  * up feature tile s are adjacent, for the fused [gate; up] projection of LlamaMLP (flash_llama_modeling.py:315-335). */
 #define B200_W4_LAYOUT_PLAIN 0
 #define B200_W4_LAYOUT_GATE_UP 1
-int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
-                      int groupsize, int layout, void* stream);
+/* row_perm (int32 [K], device) or NULL: act-order checkpoints (non-trivial g_idx; exllamav2.py:31-48 q_perm): a stable
+ * arg-sort of g_idx.  Packed row k' = checkpoint row row_perm[k']; feed the GEMM x[:, row_perm] (b200_permute_columns). */
+int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const void* scales, const int32_t* row_perm, void* packed,
+                      int64_t K, int64_t N, int groupsize, int layout, void* stream);
+/* out[t, k'] = x[t, perm[k']], fp16 [T, K] */
+int b200_permute_columns(const void* x, const int32_t* perm, void* out, int64_t T, int64_t K, void* stream);
 
 /* y[T,N] = x[T,K] . dequant(packed) (+ bias);  replaces exllamav2_kernels.gemm_half_q_half
  * (utils/gptq/exllamav2.py:14-20) for every T (no dequant-to-scratch branch, cf. :87). */
@@ -153,8 +157,8 @@ int b200_decode_advance(const int32_t* block_table, int64_t block_table_stride, 
 typedef struct {
   const void* weight;  /* fp16 [N, K], or NULL when GPTQ */
   const void* qweight; /* GPTQ: the b200_gptq_pack output for this linear, or NULL */
-  const void* qzeros;  /* unused (folded into the packed records); kept for layout stability */
-  const void* scales;  /* unused */
+  const void* perm;    /* GPTQ act-order: int32 [K] row permutation the weight was packed with (x is gathered by it), or NULL */
+  const void* _unused; /* reserved */
   const void* bias;    /* fp16 [N] or NULL */
   int64_t N, K;
   int32_t groupsize;
@@ -207,6 +211,7 @@ typedef struct {
   void* attn_out; /* [T, h d] */
   void* gate_up;  /* [T, 2 I / tp] */
   void* act;      /* [T, I / tp] */
+  void* perm_x;   /* [T, max K] scratch for the gathered activations of act-order GPTQ linears, or NULL if there are none */
   void* attn_ws;  /* b200_attn_decode_workspace_bytes */
   int64_t attn_ws_bytes;
   void* gemm_ws; /* b200_gemm_workspace_bytes (max over the model's linears), first 64 KiB zeroed once */

@@ -342,8 +342,10 @@ class LlamaOracle:
 # synthetic checkpoints and TP slicing (utils/weights.py:79-201)
 # --------------------------------------------------------------------------------------
 def make_state_dict(cfg: LlamaConfig, seed: int = 1234, quantize: Optional[str] = None,
-                    groupsize: int = 128, std: float = 0.02) -> Dict[str, torch.Tensor]:
-    """HF-named tensors. quantize='gptq' -> reference-format int4 tensors."""
+                    groupsize: int = 128, std: float = 0.02, act_order: bool = False) -> Dict[str, torch.Tensor]:
+    """HF-named tensors. quantize='gptq' -> reference-format int4 tensors.
+    act_order: every linear gets a shuffled g_idx (rows assigned to groups at random, `groupsize` rows each); projections
+    that the loader fuses (q/k/v, gate/up) share one, as utils/weights.py:131-135 requires."""
     g = torch.Generator().manual_seed(seed)
 
     def rnd(*shape):
@@ -360,10 +362,17 @@ def make_state_dict(cfg: LlamaConfig, seed: int = 1234, quantize: Optional[str] 
         shapes = {"self_attn.q_proj": (cfg.num_attention_heads * d, H), "self_attn.k_proj": (cfg.num_key_value_heads * d, H),
                   "self_attn.v_proj": (cfg.num_key_value_heads * d, H), "self_attn.o_proj": (H, cfg.num_attention_heads * d),
                   "mlp.gate_proj": (I, H), "mlp.up_proj": (I, H), "mlp.down_proj": (H, I)}
+        shuffled = {}
         for name, (n, k) in shapes.items():
             w = rnd(n, k)
             if quantize == "gptq":
                 qw, qz, sc, gi = ogptq.quantize_rtn(w, groupsize)
+                if act_order:
+                    fused = {"self_attn.q_proj": "qkv", "self_attn.k_proj": "qkv", "self_attn.v_proj": "qkv",
+                             "mlp.gate_proj": "gate_up", "mlp.up_proj": "gate_up"}.get(name, name)
+                    if fused not in shuffled:
+                        shuffled[fused] = (torch.randperm(k, generator=g) // groupsize).to(torch.int32)
+                    gi = shuffled[fused].clone()  # safetensors refuses tensors that share storage
                 sd[f"{p}.{name}.qweight"], sd[f"{p}.{name}.qzeros"] = qw, qz
                 sd[f"{p}.{name}.scales"], sd[f"{p}.{name}.g_idx"] = sc, gi
             else:

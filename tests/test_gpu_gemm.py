@@ -146,6 +146,32 @@ def test_gemm_w4a16_gate_up_layout_and_fused_silu(ops, T, I, K):
     _close(fused, ref, what=f"fused silu*up {T}x{I}x{K}")
 
 
+def test_gemm_w4a16_act_order(ops):
+    """Act-order checkpoint (shuffled g_idx, exllamav2.py:31-48): Ex4bitLinearV2 packs the rows in group order and gathers
+    the activations; result == oracle dequant with g_idx (quant_linear.py:184-192 `g = g_idx[k]`)."""
+    from tgis_b200.utils.gptq.exllamav2 import Ex4bitLinearV2
+    g = torch.Generator().manual_seed(5)
+    T, N, K, gs = 17, 384, 512, 128
+    w = torch.randn(N, K, generator=g) * 0.05
+    qweight, qzeros, scales, _ = ogptq.quantize_rtn(w, gs)
+    # a random assignment of rows to groups with exactly gs rows each; the row's nibbles keep their values
+    g_idx = (torch.randperm(K, generator=g) // gs).to(torch.int32)
+    x = torch.randn(T, K, generator=g).half()
+    ref = ogptq.gemm_half_q_half(x, qweight, qzeros, scales, g_idx, gs)
+    lin = Ex4bitLinearV2(qweight.to(DEV), qzeros.to(DEV), scales.to(DEV), g_idx.to(DEV), None, 4, gs)
+    assert lin.q_perm is not None
+    got = lin(x.to(DEV))
+    torch.cuda.synchronize()
+    _close(got, ref, what="act-order gemm")
+    # one-hot probes: row k of the dequantised matrix, bit for bit
+    wd = ogptq.dequantize(qweight, qzeros, scales, g_idx, gs)
+    ks = [0, 1, 127, 128, 300, 511]
+    xo = torch.zeros(len(ks), K, dtype=torch.float16)
+    for i, k in enumerate(ks):
+        xo[i, k] = 1.0
+    assert torch.equal(lin(xo.to(DEV)).cpu(), wd[ks])
+
+
 def test_gemm_w4a16_dequant_bit_exact(ops):
     """x = one-hot rows -> y[t] is row k_t of the dequantised matrix: must equal the oracle's fp16 W bit for bit."""
     g = torch.Generator().manual_seed(77)

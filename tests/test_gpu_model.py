@@ -25,7 +25,7 @@ def _config(cfg: oll.LlamaConfig, quantize):
         attention_bias=False, mlp_bias=False, max_position_embeddings=512, model_type="llama")
 
 
-def build_model(tmp_path, cfg, quantize, seed=1234):
+def build_model(tmp_path, cfg, quantize, seed=1234, act_order=False):
     from safetensors.torch import save_file
     import tgis_b200  # noqa: F401
     from tgis_b200.models.custom_modeling.flash_llama_modeling import FlashLlamaForCausalLM
@@ -33,7 +33,7 @@ def build_model(tmp_path, cfg, quantize, seed=1234):
     from tgis_b200.utils.paged import PagedKVCacheManager
     from tgis_b200.utils.weights import Weights
 
-    sd = oll.make_state_dict(cfg, seed=seed, quantize=quantize)
+    sd = oll.make_state_dict(cfg, seed=seed, quantize=quantize, act_order=act_order)
     path = os.path.join(tmp_path, "model.safetensors")
     save_file({k: v.contiguous() for k, v in sd.items()}, path)
     weights = Weights([path], device=DEV, dtype=torch.float16, process_group=FakeGroup(0, 1))
@@ -69,12 +69,13 @@ CASES = [
     ("gqa_d64_fp16", oll.LlamaConfig(512, 1024, 3, 8, 2, 1000), None),
     ("mha_d128_gptq", oll.LlamaConfig(256, 512, 2, 2, 2, 512), "gptq"),
     ("gqa_d128_gptq", oll.LlamaConfig(1024, 2048, 2, 8, 2, 768), "gptq"),
+    ("gqa_d128_gptq_actorder", oll.LlamaConfig(1024, 2048, 2, 8, 2, 768), "gptq"),
 ]
 
 
 @pytest.mark.parametrize("name,cfg,quantize", CASES, ids=[c[0] for c in CASES])
 def test_prefill_then_decode_matches_oracle(tmp_path, name, cfg, quantize):
-    model, oracle = build_model(str(tmp_path), cfg, quantize)
+    model, oracle = build_model(str(tmp_path), cfg, quantize, act_order=name.endswith("actorder"))
     mgr = model.kv_cache_manager
     g = torch.Generator().manual_seed(7)
     lens = [5, 17, 1, 40, 16]

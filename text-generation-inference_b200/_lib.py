@@ -35,7 +35,8 @@ SIGNATURES = {
     "b200_gemm_f16": (_I, [_P, _P, _P, _P, _L, _L, _L, _P, _P]),
     "b200_gptq_packed_bytes": (_L, [_L, _L, _I]),
     "b200_gptq_pack": (_I, [_P, _P, _P, _P, _L, _L, _I, _P]),
-    "b200_gptq_pack_ex": (_I, [_P, _P, _P, _P, _L, _L, _I, _I, _P]),
+    "b200_gptq_pack_ex": (_I, [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P]),
+    "b200_permute_columns": (_I, [_P, _P, _P, _L, _L, _P]),
     "b200_gemm_w4a16": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _P, _P]),
     "b200_gemm_w4a16_ex": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _P, _P]),
 }
@@ -43,7 +44,7 @@ SIGNATURES = {
 
 
 class B200Linear(ctypes.Structure):
-    _fields_ = [("weight", _P), ("qweight", _P), ("qzeros", _P), ("scales", _P), ("bias", _P), ("N", _L), ("K", _L),
+    _fields_ = [("weight", _P), ("qweight", _P), ("perm", _P), ("_unused", _P), ("bias", _P), ("N", _L), ("K", _L),
                 ("groupsize", ctypes.c_int32), ("layout", ctypes.c_int32)]
 
 
@@ -65,7 +66,7 @@ class B200LlamaStep(ctypes.Structure):
                 ("_pad", ctypes.c_int32), ("input_ids", _P), ("position_ids", _P), ("slot_mapping", _P), ("cu_seqlens", _P),
                 ("block_table", _P), ("block_table_stride", _L), ("context_lens", _P), ("kv_pool", _P),
                 ("kv_layer_stride_bytes", _L), ("kv_v_offset_bytes", _L), ("hidden", _P), ("residual", _P), ("normed", _P),
-                ("qkv", _P), ("attn_out", _P), ("gate_up", _P), ("act", _P), ("attn_ws", _P), ("attn_ws_bytes", _L),
+                ("qkv", _P), ("attn_out", _P), ("gate_up", _P), ("act", _P), ("perm_x", _P), ("attn_ws", _P), ("attn_ws_bytes", _L),
                 ("gemm_ws", _P), ("head_rows", _P), ("n_head_rows", _L), ("head_in", _P), ("logits", _P), ("next_ids", _P), ("banned_ids", _P)]
 
 

@@ -230,6 +230,23 @@ __global__ void __launch_bounds__(kArgmaxThreads) argmax_kernel(const __half* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// out[t, k'] = x[t, perm[k']]   (act-order GPTQ: activations follow the row order of the packed weight)
+// ------------------------------------------------------------------------------------------------
+__global__ void permute_columns_kernel(const __half* __restrict__ x, const int32_t* __restrict__ perm, __half* __restrict__ out,
+                                       int64_t K) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const __half* xr = x + (size_t)blockIdx.x * K;
+  __half* orow = out + (size_t)blockIdx.x * K;
+  for (int64_t k = threadIdx.x * 2; k < K; k += blockDim.x * 2) {  // K % 2 == 0
+    __half2 v;
+    v.x = xr[perm[k]];
+    v.y = xr[perm[k + 1]];
+    *reinterpret_cast<__half2*>(orow + k) = v;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -277,6 +294,14 @@ extern "C" int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t 
   int64_t blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   B200_LAUNCH(silu_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)gate_up, (__half*)out, I, total8);
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+extern "C" int b200_permute_columns(const void* x, const int32_t* perm, void* out, int64_t T, int64_t K, void* stream) {
+  if (T == 0 || K == 0) return B200_OK;
+  if (K % 2 != 0) { b200_set_last_error("permute_columns: K % 2 != 0"); return B200_ERR_ARG; }
+  B200_LAUNCH(permute_columns_kernel, dim3((unsigned)T), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, perm, (__half*)out, K);
   b200_count_launches(1);
   return B200_OK;
 }

@@ -641,7 +641,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
 // checkpoint tensors -> unit records.  One thread per output u32.
 __global__ void gptq_pack_kernel(const uint32_t* __restrict__ qweight, const uint32_t* __restrict__ qzeros,
                                  const __half* __restrict__ scales, uint32_t* __restrict__ packed, int64_t K, int64_t N, int groupsize,
-                                 int group_rows, int nkb, int64_t n_words_total, int half_tiles) {
+                                 int group_rows, int nkb, int64_t n_words_total, int half_tiles, const int32_t* __restrict__ row_perm) {
   const int rec_words = (kW4WordBytes + group_rows * kW4MetaRowBytes) / 4;
   const int64_t G = (K + groupsize - 1) / groupsize;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_words_total; o += (int64_t)gridDim.x * blockDim.x) {
@@ -656,9 +656,19 @@ __global__ void gptq_pack_kernel(const uint32_t* __restrict__ qweight, const uin
       const int64_t n = tile * kW4TileM + m;
       const int64_t kw = (int64_t)kb * (kW4BlockK / 8) + c * 4 + j;  // checkpoint word row: k = 8 kw .. 8 kw + 7
       if (n < N && kw * 8 < K) {
-        const uint32_t w = qweight[kw * N + n];
+        if (!row_perm) {
+          const uint32_t w = qweight[kw * N + n];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) out |= ((w >> (4 * k)) & 15u) << (4 * ((k & 1) * 4 + (k >> 1)));
+          for (int k = 0; k < 8; ++k) out |= ((w >> (4 * k)) & 15u) << (4 * ((k & 1) * 4 + (k >> 1)));
+        } else {
+          // act-order: packed row k' holds checkpoint row row_perm[k'] (rows sorted by group)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int64_t src = row_perm[kw * 8 + k];
+            const uint32_t q = (qweight[(src >> 3) * N + n] >> (4 * (src & 7))) & 15u;
+            out |= q << (4 * ((k & 1) * 4 + (k >> 1)));
+          }
+        }
       }
     } else {
       const int mr = r - kW4WordBytes / 4;
@@ -791,9 +801,12 @@ static int w4_half_tiles(int64_t N, int layout, const char* who) {
 }
 
 // qweight int32 [K/8, N], qzeros int32 [ceil(K/g), N/8], scales fp16 [ceil(K/g), N] (checkpoint layout, left untouched)
-// -> packed (b200_gptq_packed_bytes bytes, 16-byte aligned).  Groups are k // groupsize (trivial g_idx).
-extern "C" int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
-                                 int groupsize, int layout, void* stream) {
+// -> packed (b200_gptq_packed_bytes bytes, 16-byte aligned).  row_perm == NULL: groups are k // groupsize (trivial g_idx).
+// Act-order checkpoints (g_idx not sorted; exllamav2.py:31-48 builds q_perm for them): row_perm[k'] = the checkpoint row
+// stored at packed row k', a stable arg-sort of g_idx, so that packed rows k' // groupsize share a group again; the GEMM
+// is then fed x[:, row_perm] (b200_permute_columns).
+extern "C" int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const void* scales, const int32_t* row_perm, void* packed,
+                                 int64_t K, int64_t N, int groupsize, int layout, void* stream) {
   if (!w4_check_shape(N, K, groupsize, "gptq_pack")) return B200_ERR_ARG;
   if (((uintptr_t)packed & 15) != 0) { b200_set_last_error("gptq_pack: packed buffer must be 16-byte aligned"); return B200_ERR_ARG; }
   const int half_tiles = w4_half_tiles(N, layout, "gptq_pack");
@@ -805,14 +818,14 @@ extern "C" int b200_gptq_pack_ex(const void* qweight, const void* qzeros, const 
   if (blocks > 148 * 16) blocks = 148 * 16;
   gptq_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qweight, (const uint32_t*)qzeros,
                                                                         (const __half*)scales, (uint32_t*)packed, K, N, groupsize, gr,
-                                                                        nkb, n_words, half_tiles);
+                                                                        nkb, n_words, half_tiles, row_perm);
   B200_CHECK_LAUNCH();
   b200_count_launches(1);
   return B200_OK;
 }
 extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const void* scales, void* packed, int64_t K, int64_t N,
                               int groupsize, void* stream) {
-  return b200_gptq_pack_ex(qweight, qzeros, scales, packed, K, N, groupsize, 0, stream);
+  return b200_gptq_pack_ex(qweight, qzeros, scales, nullptr, packed, K, N, groupsize, 0, stream);
 }
 
 // bytes of split-K partials the int4 GEMM may write for this shape (the tile counters sit in the first 64 KiB)

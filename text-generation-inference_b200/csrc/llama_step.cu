@@ -7,10 +7,22 @@
 #include "common.cuh"
 #include "../../include/b200_tgis.h"
 
-static int linear(const B200Linear* L, const void* x, void* y, int64_t T, void* gemm_ws, void* stream) {
-  if (L->qweight)
-    return b200_gemm_w4a16_ex(x, L->qweight, L->bias, y, T, L->N, L->K, L->groupsize, L->layout, 0, gemm_ws, stream);
-  return b200_gemm_f16(x, L->weight, L->bias, y, T, L->N, L->K, gemm_ws, stream);
+// act-order GPTQ: the weight rows were packed in group order, the activations follow (exllamav2 q_perm)
+static int gathered(const B200Linear* L, const B200LlamaStep* s, const void** x, int64_t T, void* stream) {
+  if (!L->qweight || !L->perm) return B200_OK;
+  if (!s->perm_x) { b200_set_last_error("llama_step: act-order linear but no perm_x scratch"); return B200_ERR_ARG; }
+  const int st = b200_permute_columns(*x, (const int32_t*)L->perm, s->perm_x, T, L->K, stream);
+  *x = s->perm_x;
+  return st;
+}
+
+static int linear(const B200Linear* L, const B200LlamaStep* s, const void* x, void* y, int64_t T, void* stream) {
+  if (L->qweight) {
+    const int st = gathered(L, s, &x, T, stream);
+    if (st != B200_OK) return st;
+    return b200_gemm_w4a16_ex(x, L->qweight, L->bias, y, T, L->N, L->K, L->groupsize, L->layout, 0, s->gemm_ws, stream);
+  }
+  return b200_gemm_f16(x, L->weight, L->bias, y, T, L->N, L->K, s->gemm_ws, stream);
 }
 
 #define RUN(expr)            \
@@ -39,7 +51,7 @@ extern "C" int b200_llama_attn_block(const B200LlamaWeights* w, const B200LlamaS
   } else {
     RUN(b200_rmsnorm_residual(s->hidden, s->residual, L->input_ln, s->normed, s->residual, T, w->hidden_size, w->rms_eps, stream));
   }
-  RUN(linear(&L->qkv, s->normed, s->qkv, T, s->gemm_ws, stream));
+  RUN(linear(&L->qkv, s, s->normed, s->qkv, T, stream));
   char* k_pool = (char*)s->kv_pool + (size_t)layer * s->kv_layer_stride_bytes;
   char* v_pool = k_pool + s->kv_v_offset_bytes;
   RUN(b200_rope_kv_write_paged(s->qkv, w->rope_cos, w->rope_sin, s->position_ids, s->slot_mapping, k_pool, v_pool, T, w->n_heads,
@@ -55,7 +67,7 @@ extern "C" int b200_llama_attn_block(const B200LlamaWeights* w, const B200LlamaS
                                s->attn_out, (int64_t)w->n_heads * d, s->attn_ws, s->attn_ws_bytes, s->B, w->n_heads, w->n_kv_heads,
                                d, s->max_s, w->softmax_scale, stream));
   }
-  RUN(linear(&L->o, s->attn_out, s->hidden, T, s->gemm_ws, stream));
+  RUN(linear(&L->o, s, s->attn_out, s->hidden, T, stream));
   return B200_OK;
 }
 
@@ -66,13 +78,15 @@ extern "C" int b200_llama_mlp_block(const B200LlamaWeights* w, const B200LlamaSt
   RUN(b200_rmsnorm_residual(s->hidden, s->residual, L->post_ln, s->normed, s->residual, T, w->hidden_size, w->rms_eps, stream));
   if (L->gate_up.qweight && L->gate_up.layout == B200_W4_LAYOUT_GATE_UP) {
     // int4 gate|up layout: SiLU(gate) * up is the GEMM's epilogue, the [T, 2 I] intermediate never exists
-    RUN(b200_gemm_w4a16_ex(s->normed, L->gate_up.qweight, L->gate_up.bias, s->act, T, L->gate_up.N, L->gate_up.K, L->gate_up.groupsize,
+    const void* x = s->normed;
+    RUN(gathered(&L->gate_up, s, &x, T, stream));
+    RUN(b200_gemm_w4a16_ex(x, L->gate_up.qweight, L->gate_up.bias, s->act, T, L->gate_up.N, L->gate_up.K, L->gate_up.groupsize,
                            B200_W4_LAYOUT_GATE_UP, 1, s->gemm_ws, stream));
   } else {
-    RUN(linear(&L->gate_up, s->normed, s->gate_up, T, s->gemm_ws, stream));
+    RUN(linear(&L->gate_up, s, s->normed, s->gate_up, T, stream));
     RUN(b200_silu_mul(s->gate_up, s->act, T, L->gate_up.N / 2, stream));
   }
-  RUN(linear(&L->down, s->act, s->hidden, T, s->gemm_ws, stream));
+  RUN(linear(&L->down, s, s->act, s->hidden, T, stream));
   return B200_OK;
 }
 
@@ -91,7 +105,7 @@ extern "C" int b200_llama_head(const B200LlamaWeights* w, const B200LlamaStep* s
   head.weight = w->lm_head;
   head.N = w->vocab_rows_head;
   head.K = w->hidden_size;
-  RUN(linear(&head, x, s->logits, rows, s->gemm_ws, stream));
+  RUN(linear(&head, s, x, s->logits, rows, stream));
   if (s->next_ids) RUN(b200_argmax(s->logits, s->next_ids, rows, w->vocab_rows_head, w->vocab_rows_head, s->banned_ids, stream));
   return B200_OK;
 }

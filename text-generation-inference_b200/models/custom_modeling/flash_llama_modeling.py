@@ -123,12 +123,13 @@ def _fill_linear(dst: _lib.B200Linear, lin, gate_up: bool = False) -> None:
     if isinstance(lin, Ex4bitLinearV2):
         lin.post_init(layout=1 if gate_up else 0)  # gate|up record order: SiLU * up fuses into the GEMM epilogue
         dst.weight = None
-        dst.qweight, dst.qzeros, dst.scales = lin.q_handle.data_ptr(), None, None
+        dst.qweight = lin.q_handle.data_ptr()
+        dst.perm = lin.q_perm.data_ptr() if lin.q_perm is not None else None
         dst.N, dst.K, dst.groupsize = lin.outfeatures, lin.infeatures, lin.group_size
         dst.layout = lin.pack_layout
     elif isinstance(lin, FastLinear):
         dst.weight = lin.weight.data_ptr()
-        dst.qweight = dst.qzeros = dst.scales = None
+        dst.qweight = dst.perm = None
         dst.N, dst.K, dst.groupsize = lin.weight.shape[0], lin.weight.shape[1], 0
     else:
         raise TypeError(type(lin))
@@ -158,6 +159,8 @@ class StepScratch:
                              qkv=torch.empty(cap, nqkv, **f16), attn_out=torch.empty(cap, m.model.num_heads * d, **f16),
                              gate_up=torch.empty(cap, 2 * I, **f16), act=torch.empty(cap, I, **f16),
                              head_in=torch.empty(cap, H, **f16))
+            if m.has_act_order:  # gathered activations of act-order GPTQ linears
+                self.bufs["perm_x"] = torch.empty(cap, max(K for _, K in m.linear_shapes), **f16)
             self.cap = cap
             self.version += 1
             lib = _lib.load()
@@ -210,6 +213,7 @@ class FlashLlamaForCausalLM(nn.Module):
         n = len(m.layers)
         arr = (_lib.B200LlamaLayer * n)()
         shapes = []
+        self.has_act_order = False
         for i, layer in enumerate(m.layers):
             arr[i].input_ln = layer.input_layernorm.weight.data_ptr()
             arr[i].post_ln = layer.post_attention_layernorm.weight.data_ptr()
@@ -217,6 +221,7 @@ class FlashLlamaForCausalLM(nn.Module):
                               ("gate_up", layer.mlp.gate_up_proj.linear), ("down", layer.mlp.down_proj.linear)):
                 dst = getattr(arr[i], name)
                 _fill_linear(dst, lin, gate_up=(name == "gate_up"))
+                self.has_act_order |= bool(dst.perm)
                 shapes.append((dst.N, dst.K))
         head = self.lm_head.linear
         assert isinstance(head, FastLinear), "GPTQ never quantizes the head (utils/layers.py:236-237)"
@@ -255,6 +260,7 @@ class FlashLlamaForCausalLM(nn.Module):
         s.kv_pool, s.kv_layer_stride_bytes, s.kv_v_offset_bytes = mgr.pool.data_ptr(), mgr.layer_stride_bytes, mgr.v_offset_bytes
         for k in ("hidden", "residual", "normed", "qkv", "attn_out", "gate_up", "act", "head_in"):
             setattr(s, k, sc.bufs[k].data_ptr())
+        s.perm_x = sc.bufs["perm_x"].data_ptr() if "perm_x" in sc.bufs else None
         if inputs_embeds is not None:
             sc.bufs["hidden"][:T].copy_(inputs_embeds)
         s.attn_ws, s.attn_ws_bytes = sc.attn_ws.data_ptr(), sc.attn_ws.numel()

@@ -157,8 +157,18 @@ def gemm_f16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
 W4_LAYOUT_PLAIN, W4_LAYOUT_GATE_UP = 0, 1
 
 
+def permute_columns(x: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """out[t, k'] = x[t, perm[k']] (act-order GPTQ: activations follow the packed weight's row order)."""
+    _req(x, torch.float16, "x")
+    _req(perm, torch.int32, "perm")
+    assert x.is_contiguous() and perm.is_contiguous() and perm.shape[0] == x.shape[1]
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().b200_permute_columns(_ptr(x), _ptr(perm), _ptr(out), x.shape[0], x.shape[1], _stream()), "permute_columns")
+    return out
+
+
 def gptq_pack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, groupsize: int,
-              layout: int = W4_LAYOUT_PLAIN) -> torch.Tensor:
+              layout: int = W4_LAYOUT_PLAIN, row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Checkpoint GPTQ tensors of one linear -> the kernel's unit-record stream (uint8 tensor).
     layout = W4_LAYOUT_GATE_UP pairs gate tile s with up tile s (fused [gate; up] projection, N = 2 I, I % 128 == 0)."""
     _req(qweight, torch.int32, "qweight")
@@ -172,8 +182,11 @@ def gptq_pack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
     if nbytes < 0:
         raise _lib.B200Error(f"gptq_pack: {lib.b200_last_error().decode()}")
     packed = torch.empty(nbytes, dtype=torch.uint8, device=qweight.device)
-    _lib.check(lib.b200_gptq_pack_ex(_ptr(qweight), _ptr(qzeros), _ptr(scales), _ptr(packed), K, N, groupsize, layout, _stream()),
-               "gptq_pack")
+    if row_perm is not None:
+        _req(row_perm, torch.int32, "row_perm")
+        assert row_perm.is_contiguous() and row_perm.shape[0] == K
+    _lib.check(lib.b200_gptq_pack_ex(_ptr(qweight), _ptr(qzeros), _ptr(scales), _ptr(row_perm), _ptr(packed), K, N, groupsize,
+                                     layout, _stream()), "gptq_pack")
     return packed
 
 

@@ -33,10 +33,16 @@ class Ex4bitLinearV2(nn.Module):
         self.height = self.infeatures
         self.width = self.outfeatures
         assert self.infeatures % 32 == 0 and self.outfeatures % 32 == 0  # exllamav2.py:118-119
+        # act-order (exllamav2.py:31-48): a g_idx that is neither k // groupsize nor all zeros gets a row permutation
+        self.q_perm = None
         if g_idx is not None and groupsize > 0:
-            trivial = torch.equal(g_idx.cpu().to(torch.int64), torch.arange(self.infeatures) // groupsize)
-            if not trivial and not bool((g_idx == 0).all()):
-                raise NotImplementedError("act-order (non-trivial g_idx) checkpoints are not supported yet")
+            gi = g_idx.to(torch.int64)
+            trivial = torch.equal(gi.cpu(), torch.arange(self.infeatures) // groupsize)
+            if not trivial and not bool((gi == 0).all()):
+                counts = torch.bincount(gi.cpu(), minlength=(self.infeatures + groupsize - 1) // groupsize)
+                if not bool((counts[:-1] == groupsize).all()):
+                    raise NotImplementedError("act-order g_idx with groups of unequal size")
+                self.q_perm = torch.argsort(gi, stable=True).to(torch.int32).contiguous()
 
     def post_init(self, temp_dq=None, layout: int = 0):
         """exllamav2.py:124-137 (make_q_matrix): one-time conversion to the kernel layout; the checkpoint tensors are
@@ -47,8 +53,10 @@ class Ex4bitLinearV2(nn.Module):
             assert self.qweight.device.type == "cuda"
             if layout == 1 and self.outfeatures % 256 != 0:
                 layout = 0
+            if self.q_perm is not None:
+                self.q_perm = self.q_perm.to(self.qweight.device)
             self.q_handle = _ops().gptq_pack(self.qweight.contiguous(), self.qzeros.contiguous(), self.scales.contiguous(),
-                                             self.group_size, layout)
+                                             self.group_size, layout, self.q_perm)
             self.pack_layout = layout
             self.qweight = self.qzeros = self.scales = None
 
@@ -57,6 +65,8 @@ class Ex4bitLinearV2(nn.Module):
             self.post_init()
         out_shape = x.shape[:-1] + (self.outfeatures,)
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        if self.q_perm is not None:
+            x2 = _ops().permute_columns(x2, self.q_perm)
         out = _ops().gemm_w4a16(x2, self.q_handle, self.outfeatures, self.group_size, self.bias, layout=self.pack_layout)
         return out.view(out_shape)
 
