@@ -63,6 +63,21 @@ int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* sin, const 
                              const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads, int n_kv_heads,
                              int head_dim, void* stream);
 
+/* same with a partial rotation (GPT-NeoX rotary_pct < 1): rotary_dim = 2 * cos.shape[-1] (utils/layers.py:467-469), tables
+ * [max_pos, rotary_dim/2]; elements from rotary_dim on pass through. */
+int b200_rope_kv_write_paged_ex(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
+                                const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads, int n_kv_heads,
+                                int head_dim, int rotary_dim, void* stream);
+
+/* ---- fused residual-add + LayerNorm: FastLayerNorm.forward (utils/layers.py:360-392 ->
+ * dropout_layer_norm.dropout_add_ln_fwd(h, residual, gamma, beta, ..., eps, 1.0, 0, None, False, False)), the norm of the
+ * GPT-NeoX family (flash_neox_modeling.py:202-281).  residual / beta / residual_out may be NULL. */
+int b200_layernorm_residual(const void* h, const void* residual, const void* gamma, const void* beta, void* normed_out,
+                            void* residual_out, int64_t T, int64_t H, float eps, void* stream);
+
+/* ---- GELU on n fp16 values (FlashMLP.act, flash_neox_modeling.py:186-196); approximate_tanh for gelu_fast / gelu_pytorch_tanh */
+int b200_gelu(const void* x, void* out, int64_t n, int approximate_tanh, void* stream);
+
 /* ---- SiLU(gate) * up   (flash_llama_modeling.py:332-335); gate_up [T, 2, I] -> out [T, I] */
 int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t I, void* stream);
 

@@ -87,3 +87,79 @@ def test_tp2_generate_matches_oracle(tmp_path, quantize):
         assert res[0][b][:n] == ref[b].tolist()[:n], f"sequence {b}: {res[0][b]} vs oracle {ref[b].tolist()}"
         total += n
     assert total >= 12
+
+
+def _neox_worker(rank, world, port, path, cfg_kwargs, prompts, n_new, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import types
+    import tgis_b200  # noqa: F401
+    from tgis_b200 import pb
+    from tgis_b200.inference_engine import InferenceEngine
+    from tgis_b200.models.flash_causal_lm import FlashCausalLM
+    from tgis_b200.utils.synthetic import make_tokenizer
+
+    cfg = types.SimpleNamespace(model_type="gpt_neox", quantize=None, max_position_embeddings=256, eos_token_id=2, pad_token_id=0,
+                                bos_token_id=1, **cfg_kwargs)
+    tok = make_tokenizer(cfg.vocab_size)
+    engine = InferenceEngine(os.path.dirname(path), None, torch.float16, None, cfg, 256, tokenizer=tok)
+    model = FlashCausalLM(os.path.dirname(path), None, "tgis_native", torch.float16, None, cfg, engine=engine, num_kv_blocks=64)
+    reqs = [pb.Request(id=i, inputs=" ".join("test" if t == 3 else f"<tok{t}>" for t in p), input_length=len(p), truncate=False,
+                       max_output_length=n_new, parameters=pb.NextTokenChooserParameters(temperature=0.0, top_p=1.0))
+            for i, p in enumerate(prompts)]
+    got = [[] for _ in prompts]
+    with torch.inference_mode():
+        batch, _ = model.batch_type.from_pb(pb.Batch(id=0, requests=reqs), tok, torch.float16, model.device, None, None, True)
+        out = model.generate_token(batch, first=True)
+        for _ in range(n_new - 1):
+            for t in out[0]:
+                got[t.request_id].append(t.token_id)
+            out = model.generate_token(batch)
+        for t in out[0]:
+            got[t.request_id].append(t.token_id)
+    torch.cuda.synchronize()
+    q.put((rank, got))
+    q.close()
+    q.join_thread()
+    os._exit(0)
+
+
+@pytest.mark.parametrize("parallel_residual", [True, False])
+def test_tp2_neox_generate_matches_oracle(tmp_path, parallel_residual):
+    """Flash GPT-NeoX sharded over 2 GPUs (flash_neox_modeling.py:40-80, 232-260: heads and MLP columns per rank, ONE
+    all-reduce per layer with the parallel residual, two otherwise) against the single-rank oracle; ids must agree up to the
+    first step whose top-2 gap is within 8 fp16 ulp (the per-rank fp16 partial sums differ from a single-rank product)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from safetensors.torch import save_file
+    from oracle import neox as onx
+    from tests.test_gpu_generate import _prompts
+    kw = dict(hidden_size=256, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4, vocab_size=512, rotary_pct=0.25,
+              rotary_emb_base=10000.0, layer_norm_eps=1e-5, use_parallel_residual=parallel_residual, hidden_act="gelu")
+    cfg = onx.NeoXConfig(256, 1024, 2, 4, 512, rotary_pct=0.25, use_parallel_residual=parallel_residual)
+    sd = onx.make_state_dict(cfg, seed=31, std=0.06)
+    path = os.path.join(str(tmp_path), "model.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    prompts = _prompts(6, [9, 20, 3], 512)
+    n_new = 6
+    ref, ref_logits = onx.NeoXOracle(cfg, sd).generate_greedy(prompts, n_new)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_neox_worker, args=(r, 2, port, path, kw, prompts, n_new, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        if p.exitcode is None:
+            p.kill()
+    assert res[0] == res[1], "ranks diverged"
+    total = 0
+    for b in range(len(prompts)):
+        for s in range(n_new):
+            top2 = ref_logits[s][b].float().topk(2).values
+            if (top2[0] - top2[1]) <= 8 * max(abs(top2[0].item()), 1.0) * 2.0 ** -10:
+                break
+            assert res[0][b][s] == int(ref[b, s]), f"sequence {b} step {s}: {res[0][b]} vs oracle {ref[b].tolist()}"
+            total += 1
+    assert total >= 9

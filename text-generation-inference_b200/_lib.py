@@ -19,6 +19,9 @@ SIGNATURES = {
     "b200_debug_w4_flags": (None, [_I]),
     "b200_rmsnorm_residual": (_I, [_P, _P, _P, _P, _P, _L, _L, _F, _P]),
     "b200_rope_kv_write_paged": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "b200_rope_kv_write_paged_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "b200_layernorm_residual": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _F, _P]),
+    "b200_gelu": (_I, [_P, _P, _L, _I, _P]),
     "b200_silu_mul": (_I, [_P, _P, _L, _L, _P]),
     "b200_embedding": (_I, [_P, _P, _P, _L, _L, _L, _L, _P]),
     "b200_argmax": (_I, [_P, _P, _L, _L, _L, _P, _P]),

@@ -106,19 +106,37 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ qkv, const __half* __r
   pdl_wait();
   const int t = blockIdx.x;
   const int head = blockIdx.y;  // [0,h): q, [h,h+kv): k, [h+kv, h+2kv): v
-  const int j = threadIdx.x;    // pair index 0..d/2-1
+  const int j = threadIdx.x;    // 0..d/2-1: this thread owns elements j and j + d/2 of the head row
   __half* base = qkv + ((size_t)t * (n_heads + 2 * n_kv) + head) * kHeadDim;
   const bool is_v = head >= n_heads + n_kv;
   __half lo = base[j], hi = base[j + kHeadDim / 2];
   if (!is_v) {
-    // rotary_dim = cos.shape[-1] = rot_half: x1 = x[:rot_half], x2 = x[rot_half:2*rot_half]
-    // kernel is instantiated for full rotation (rot_half == d/2), the Llama case.
+    // rotary_dim = cos.shape[-1] * 2 = 2 rot_half (utils/layers.py:467-469): pairs (x[i], x[i + rot_half]), i < rot_half;
+    // elements from 2 rot_half on pass through (GPT-NeoX rotary_pct < 1).  Full rotation (Llama): rot_half == d/2 and
+    // the pair is exactly this thread's (lo, hi).
     const int64_t pos = position_ids[t];
-    const float c = __half2float(cos_t[pos * rot_half + j]);
-    const float s = __half2float(sin_t[pos * rot_half + j]);
-    const float x1 = __half2float(lo), x2 = __half2float(hi);
-    lo = __float2half_rn(x1 * c - x2 * s);
-    hi = __float2half_rn(x1 * s + x2 * c);
+    if (rot_half == kHeadDim / 2) {
+      const float c = __half2float(cos_t[pos * rot_half + j]);
+      const float s = __half2float(sin_t[pos * rot_half + j]);
+      const float x1 = __half2float(lo), x2 = __half2float(hi);
+      lo = __float2half_rn(x1 * c - x2 * s);
+      hi = __float2half_rn(x1 * s + x2 * c);
+    } else {
+      __shared__ __half row[kHeadDim];
+      row[j] = lo;
+      row[j + kHeadDim / 2] = hi;
+      __syncthreads();
+      if (j < rot_half) {
+        const float c = __half2float(cos_t[pos * rot_half + j]);
+        const float s = __half2float(sin_t[pos * rot_half + j]);
+        const float x1 = __half2float(row[j]), x2 = __half2float(row[j + rot_half]);
+        row[j] = __float2half_rn(x1 * c - x2 * s);
+        row[j + rot_half] = __float2half_rn(x1 * s + x2 * c);
+      }
+      __syncthreads();
+      lo = row[j];
+      hi = row[j + kHeadDim / 2];
+    }
     base[j] = lo;
     base[j + kHeadDim / 2] = hi;
   }
@@ -133,6 +151,85 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ qkv, const __half* __r
     const int e_lo = j, e_hi = j + kHeadDim / 2;
     *reinterpret_cast<__half*>(tile + kv_swizzled_chunk_offset<kHeadDim>(tok, e_lo >> 3) + (e_lo & 7) * 2) = lo;
     *reinterpret_cast<__half*>(tile + kv_swizzled_chunk_offset<kHeadDim>(tok, e_hi >> 3) + (e_hi & 7) * 2) = hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual-add + LayerNorm (FastLayerNorm, utils/layers.py:360-392 -> dropout_layer_norm.dropout_add_ln_fwd):
+// x = h + residual in fp32, residual_out = fp16(x), normed = fp16((x - mean) * rstd * gamma + beta), fp32 statistics.
+// One CTA per token row.
+// ------------------------------------------------------------------------------------------------
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) layernorm_residual_kernel(const __half* __restrict__ h, const __half* __restrict__ residual,
+                                                                        const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                                                        __half* __restrict__ normed, __half* __restrict__ res_out, int H,
+                                                                        float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of the summed row
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const __half* hp = h + (size_t)row * H;
+  const __half* rp = residual ? residual + (size_t)row * H : nullptr;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // red[] reuse
+    if (lane_id() == 0) red[warp_id()] = v;
+    __syncthreads();
+    float t = lane_id() < kThreads / 32 ? red[lane_id()] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+  };
+  float sum = 0.f;
+  for (int i = threadIdx.x * 2; i < H; i += kThreads * 2) {
+    float2 x = __half22float2(*reinterpret_cast<const __half2*>(hp + i));
+    if (rp) {
+      const float2 r = __half22float2(*reinterpret_cast<const __half2*>(rp + i));
+      x.x += r.x;
+      x.y += r.y;
+      if (res_out) *reinterpret_cast<__half2*>(res_out + (size_t)row * H + i) = __floats2half2_rn(x.x, x.y);
+    }
+    xs[i] = x.x;
+    xs[i + 1] = x.y;
+    sum += x.x + x.y;
+  }
+  const float mean = block_sum(sum) / H;
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < H; i += kThreads) {
+    const float d = xs[i] - mean;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(sq) / H + eps);
+  for (int i = threadIdx.x * 2; i < H; i += kThreads * 2) {
+    const float2 g = __half22float2(*reinterpret_cast<const __half2*>(gamma + i));
+    const float2 b = beta ? __half22float2(*reinterpret_cast<const __half2*>(beta + i)) : make_float2(0.f, 0.f);
+    *reinterpret_cast<__half2*>(normed + (size_t)row * H + i) =
+        __floats2half2_rn((xs[i] - mean) * rstd * g.x + b.x, (xs[i + 1] - mean) * rstd * g.y + b.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out = gelu(x) on fp16 (fp32 math, one rounding: torch's fp16 GELU); tanh approximation for gelu_fast / gelu_pytorch_tanh
+// (flash_neox_modeling.py:186-196)
+// ------------------------------------------------------------------------------------------------
+__global__ void gelu_kernel(const __half* __restrict__ x, __half* __restrict__ out, int64_t n2, int approximate_tanh) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = __half22float2(reinterpret_cast<const __half2*>(x)[i]);
+    float2 r;
+    if (approximate_tanh) {
+      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+      r.x = 0.5f * v.x * (1.f + tanhf(k0 * (v.x + k1 * v.x * v.x * v.x)));
+      r.y = 0.5f * v.y * (1.f + tanhf(k0 * (v.y + k1 * v.y * v.y * v.y)));
+    } else {
+      r.x = 0.5f * v.x * (1.f + erff(v.x * 0.7071067811865476f));
+      r.y = 0.5f * v.y * (1.f + erff(v.y * 0.7071067811865476f));
+    }
+    reinterpret_cast<__half2*>(out)[i] = __floats2half2_rn(r.x, r.y);
   }
 }
 
@@ -267,22 +364,60 @@ extern "C" int b200_rmsnorm_residual(const void* h, const void* residual, const 
   return B200_OK;
 }
 
-extern "C" int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
-                                        const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads,
-                                        int n_kv_heads, int head_dim, void* stream) {
+extern "C" int b200_rope_kv_write_paged_ex(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
+                                           const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads,
+                                           int n_kv_heads, int head_dim, int rotary_dim, void* stream) {
   if (T == 0) return B200_OK;
+  if (rotary_dim <= 0 || rotary_dim > head_dim || rotary_dim % 2 != 0) {
+    b200_set_last_error("rope_kv_write_paged: rotary_dim must be even and in (0, head_dim]");
+    return B200_ERR_ARG;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)T, n_heads + 2 * n_kv_heads);
   if (head_dim == 128) {
     B200_LAUNCH(rope_kv_write_kernel<128>, grid, dim3(64), 0, st, (__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids,
-                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 64);
+                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, rotary_dim / 2);
   } else if (head_dim == 64) {
     B200_LAUNCH(rope_kv_write_kernel<64>, grid, dim3(32), 0, st, (__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids,
-                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, 32);
+                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, rotary_dim / 2);
   } else {
     b200_set_last_error("rope_kv_write_paged: head_dim must be 64 or 128");
     return B200_ERR_UNSUPPORTED;
   }
+  b200_count_launches(1);
+  return B200_OK;
+}
+extern "C" int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
+                                        const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads,
+                                        int n_kv_heads, int head_dim, void* stream) {
+  return b200_rope_kv_write_paged_ex(qkv, cos, sin, position_ids, slot_mapping, k_pool, v_pool, T, n_heads, n_kv_heads, head_dim,
+                                     head_dim, stream);
+}
+
+extern "C" int b200_layernorm_residual(const void* h, const void* residual, const void* gamma, const void* beta, void* normed_out,
+                                       void* residual_out, int64_t T, int64_t H, float eps, void* stream) {
+  if (T == 0) return B200_OK;
+  if (H % 2 != 0 || H * 4 > 200 * 1024) { b200_set_last_error("layernorm_residual: need H % 2 == 0 and H <= 51200"); return B200_ERR_ARG; }
+  constexpr int kThreads = 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(layernorm_residual_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  B200_LAUNCH(layernorm_residual_kernel<kThreads>, dim3((unsigned)T), dim3(kThreads), (size_t)H * 4, (cudaStream_t)stream,
+              (const __half*)h, (const __half*)residual, (const __half*)gamma, (const __half*)beta, (__half*)normed_out,
+              (__half*)residual_out, (int)H, eps);
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+extern "C" int b200_gelu(const void* x, void* out, int64_t n, int approximate_tanh, void* stream) {
+  if (n == 0) return B200_OK;
+  if (n % 2 != 0) { b200_set_last_error("gelu: n % 2 != 0"); return B200_ERR_ARG; }
+  int64_t blocks = (n / 2 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  B200_LAUNCH(gelu_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (__half*)out, n / 2,
+              approximate_tanh);
   b200_count_launches(1);
   return B200_OK;
 }

@@ -3,7 +3,7 @@ process group, opens the safetensors shards with the TP slicing rules and builds
 
 Mirrors /root/reference/server/text_generation_server/inference_engine/engine.py:11-37 (`BaseInferenceEngine`:
 config/tokenizer loading, RANK / WORLD_SIZE, device = rank % device_count) and inference_engine/tgis_native.py:24-139.
-Only the flash decoder families of the hot path exist here (llama); other model types raise NotImplementedError.
+Only the flash decoder families of the hot path exist here (llama, gpt_neox); other model types raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -17,7 +17,7 @@ import torch.distributed
 from .utils.dist import initialize_torch_distributed
 from .utils.weights import Weights
 
-FLASH_TYPES = ["llama"]
+FLASH_TYPES = ["llama", "gpt_neox"]
 
 
 def local_weight_files(model_path: str, extension: str = ".safetensors"):
@@ -54,6 +54,9 @@ class InferenceEngine:
                 aliases = {"lm_head.weight": ["model.embed_tokens.weight"]}
             from .models.custom_modeling.flash_llama_modeling import FlashLlamaForCausalLM
             model_class = FlashLlamaForCausalLM
+        elif model_type == "gpt_neox":  # tgis_native.py:75-79
+            from .models.custom_modeling.flash_neox_modeling import FlashGPTNeoXForCausalLM
+            model_class = FlashGPTNeoXForCausalLM
         self._config.quantize = quantize
         self.process_group = initialize_torch_distributed(self.world_size, self.rank)
         self.master = self.rank == 0

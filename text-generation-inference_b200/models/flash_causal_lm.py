@@ -217,7 +217,8 @@ class FlashCausalLM(Model):
             num_kv_blocks = int(os.environ["KV_CACHE_MANAGER_NUM_GPU_BLOCKS"])  # paged_causal_lm.py:310-311
         world = getattr(engine, "world_size", 1)
         self.kv_cache_manager = PagedKVCacheManager(
-            cfg.num_hidden_layers, cfg.num_attention_heads, cfg.hidden_size, kv_heads=cfg.num_key_value_heads,
+            cfg.num_hidden_layers, cfg.num_attention_heads, cfg.hidden_size,
+            kv_heads=getattr(cfg, "num_key_value_heads", None) or cfg.num_attention_heads,
             tensor_parallel_size=world, dtype=dtype, device=self.device, total_num_gpu_blocks=num_kv_blocks, block_size=16)
         self.model.kv_cache_manager = self.kv_cache_manager
 
@@ -276,6 +277,8 @@ class FlashCausalLM(Model):
     def _can_fuse_greedy(self, batch) -> bool:
         """All-greedy batch with no per-token details on a single rank: arg-max (with the min_new_tokens EOS mask)
         runs inside the step and the ids chain device-to-device; the host reads back B ids per step."""
+        if not hasattr(self.model, "make_step"):  # families without the C++ step runtime (flash GPT-NeoX) run op by op
+            return False
         if not batch.next_token_chooser.is_plain_greedy:
             return False
         return not any(r.details.logprobs or r.details.ranks or r.details.top_n_toks for r in batch.requests)

@@ -45,16 +45,44 @@ def rmsnorm_residual(h: torch.Tensor, residual: Optional[torch.Tensor], gamma: t
     return normed, (res_out if res_out is not None else h)
 
 
+def layernorm_residual(h: torch.Tensor, residual: Optional[torch.Tensor], gamma: torch.Tensor, beta: Optional[torch.Tensor],
+                       eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(normed, residual_out) — FastLayerNorm.forward semantics (utils/layers.py:360-392)."""
+    _req(h, torch.float16, "h")
+    h = h.contiguous()
+    T, H = h.shape
+    normed = torch.empty_like(h)
+    if residual is not None:
+        residual = residual.contiguous()
+        res_out = torch.empty_like(h)
+    else:
+        res_out = None
+    _lib.check(_lib.load().b200_layernorm_residual(_ptr(h), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(normed), _ptr(res_out),
+                                                   T, H, float(eps), _stream()), "layernorm_residual")
+    return normed, (res_out if res_out is not None else h)
+
+
+def gelu(x: torch.Tensor, approximate_tanh: bool = False) -> torch.Tensor:
+    _req(x, torch.float16, "x")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().b200_gelu(_ptr(x), _ptr(out), x.numel(), int(approximate_tanh), _stream()), "gelu")
+    return out
+
+
 def rope_kv_write_paged(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position_ids: torch.Tensor,
                         slot_mapping: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, n_heads: int,
-                        n_kv_heads: int, head_dim: int) -> None:
+                        n_kv_heads: int, head_dim: int, rotary_dim: Optional[int] = None) -> None:
+    """cos/sin: fp16 tables [max_pos, rotary_dim/2]; rotary_dim defaults to head_dim (Llama), smaller = partial (NeoX)."""
     _req(qkv, torch.float16, "qkv")
     _req(position_ids, torch.int64, "position_ids")
     _req(slot_mapping, torch.int64, "slot_mapping")
     assert qkv.is_contiguous() and cos.is_contiguous() and sin.is_contiguous()
     T = qkv.shape[0]
-    _lib.check(_lib.load().b200_rope_kv_write_paged(_ptr(qkv), _ptr(cos), _ptr(sin), _ptr(position_ids), _ptr(slot_mapping),
-                                                    _ptr(k_pool), _ptr(v_pool), T, n_heads, n_kv_heads, head_dim, _stream()),
+    rd = head_dim if rotary_dim is None else rotary_dim
+    assert cos.shape[-1] * 2 == rd
+    _lib.check(_lib.load().b200_rope_kv_write_paged_ex(_ptr(qkv), _ptr(cos), _ptr(sin), _ptr(position_ids), _ptr(slot_mapping),
+                                                       _ptr(k_pool), _ptr(v_pool), T, n_heads, n_kv_heads, head_dim, rd, _stream()),
                "rope_kv_write_paged")
 
 

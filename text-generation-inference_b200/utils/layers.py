@@ -2,7 +2,7 @@
 
 Mirrors /root/reference/server/text_generation_server/utils/layers.py: `FastLinear` (:88-111), `get_linear` (:172-203),
 `TensorParallelHead` (:215-277), `TensorParallelColumnLinear` / `TensorParallelRowLinear` (:280-322),
-`TensorParallelEmbedding` (:325-357), `PositionRotaryEmbedding` (:406-481).  Same names, constructor arguments and
+`TensorParallelEmbedding` (:325-357), `FastLayerNorm` (:360-396), `PositionRotaryEmbedding` (:406-481).  Same names, constructor arguments and
 sharding behaviour; the CUDA work goes through the C ABI (ops.py), collectives through torch.distributed (NCCL).
 """
 from __future__ import annotations
@@ -145,6 +145,24 @@ class TensorParallelEmbedding(nn.Module):
         if self.reduce and self.process_group.size() > 1:
             torch.distributed.all_reduce(out, group=self.process_group)
         return out.view(*input.shape, -1)
+
+
+class FastLayerNorm(nn.Module):
+    """Residual-add + LayerNorm in one kernel (utils/layers.py:360-396: FastLayerNorm over dropout_layer_norm).
+    forward(hidden_states, residual=None) -> (normed, residual_out); residual None -> residual_out is hidden_states."""
+
+    def __init__(self, weight, bias, eps: float):
+        super().__init__()
+        self.weight = nn.Parameter(weight.contiguous(), requires_grad=False)
+        self.bias = nn.Parameter(bias.contiguous(), requires_grad=False) if bias is not None else None
+        self.eps = eps
+
+    @classmethod
+    def load(cls, prefix: str, weights, eps: float):
+        return cls(weights.get_tensor(f"{prefix}.weight"), weights.get_tensor(f"{prefix}.bias"), eps)
+
+    def forward(self, hidden_states, residual=None):
+        return _ops().layernorm_residual(hidden_states, residual, self.weight, self.bias, self.eps)
 
 
 class PositionRotaryEmbedding(nn.Module):
