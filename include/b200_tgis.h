@@ -78,6 +78,13 @@ int b200_layernorm_residual(const void* h, const void* residual, const void* gam
 /* ---- GELU on n fp16 values (FlashMLP.act, flash_neox_modeling.py:186-196); approximate_tanh for gelu_fast / gelu_pytorch_tanh */
 int b200_gelu(const void* x, void* out, int64_t n, int approximate_tanh, void* stream);
 
+/* ---- masked softmax over rows of attention scores [rows, kv] (fp16, or fp32 when is_fp32): replaces
+ * forward_masked_softmax_kernel of server/custom_kernels/custom_kernels/fused_attention_cuda.cu:28-107 (and the identical
+ * kernel of fused_bloom_attention_cuda.cu), the non-flash BLOOM / GPT-NeoX attention (bloom_modeling.py:394,
+ * neox_modeling.py:214).  mask: bool [rows, kv], non-zero = excluded; fp32 softmax over the rest, excluded positions and
+ * all-excluded rows give 0.  No kv_length limit (the reference kernel stops at 4096). */
+int b200_masked_softmax(const void* scores, const void* mask, void* out, int64_t rows, int64_t kv, int is_fp32, void* stream);
+
 /* ---- SiLU(gate) * up   (flash_llama_modeling.py:332-335); gate_up [T, 2, I] -> out [T, I] */
 int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t I, void* stream);
 

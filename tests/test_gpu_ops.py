@@ -191,3 +191,38 @@ def test_attn_prefill_varlen(ops, h, kv, d, causal):
                                   torch.tensor(cu, dtype=torch.int32, device=DEV), max(lens), scale, causal)
     torch.cuda.synchronize()
     _close(got, ref, rel=2e-3, what=f"attn_prefill h{h} kv{kv} d{d} causal={causal}")
+
+
+def test_masked_softmax_and_fused_attention(ops):
+    """b200_masked_softmax vs the restated semantics of forward_masked_softmax_kernel (custom_kernels/fused_attention_cuda.cu:28-107):
+    fp32 softmax over unmasked positions, masked -> 0, all-masked row -> zeros; kv beyond the reference's 4096 limit; and the
+    `fused_attention_cuda.forward` wrapper vs eager attention."""
+    from tgis_b200.custom_kernels import fused_attention_cuda
+    g = torch.Generator().manual_seed(4)
+    for dtype, kv in ((torch.float16, 37), (torch.float32, 300), (torch.float16, 5000)):
+        rows = 19
+        sc = (3 * torch.randn(rows, kv, generator=g)).to(dtype)
+        mask = torch.rand(rows, kv, generator=g) < 0.3
+        mask[3] = True  # an all-masked row
+        got = ops.masked_softmax(sc.to(DEV), mask.to(DEV)).cpu()
+        ref = torch.softmax(sc.float().masked_fill(mask, float("-inf")), -1)
+        ref = torch.nan_to_num(ref, nan=0.0).masked_fill(mask, 0.0).to(dtype)
+        assert torch.equal(got[3], torch.zeros(kv, dtype=dtype))
+        assert (got.float() - ref.float()).abs().max().item() <= (1e-3 if dtype == torch.float16 else 1e-6)
+    B, h, q, past, d = 2, 3, 4, 6, 64
+    query = torch.randn(B, h, q, d, generator=g).half()
+    key = torch.randn(B, h, q, d, generator=g).half()
+    value = torch.randn(B, h, q, d, generator=g).half()
+    pk = torch.randn(B, h, past, d, generator=g).half()
+    pv = torch.randn(B, h, past, d, generator=g).half()
+    kvl = past + q
+    causal = torch.ones(q, kvl, dtype=torch.bool).triu(past + 1)[None, None].expand(B, 1, q, kvl)
+    ctx, present, probs = fused_attention_cuda.forward(query.to(DEV), key.to(DEV), value.to(DEV), [pk.to(DEV), pv.to(DEV)], causal.to(DEV),
+                                                       None, d ** -0.5, h, True)
+    k_all, v_all = torch.cat([pk, key], 2).float(), torch.cat([pv, value], 2).float()
+    s = (query.float() * d ** -0.5) @ k_all.transpose(-1, -2)
+    p = torch.softmax(s.masked_fill(causal, float("-inf")), -1)
+    ref_ctx = (p @ v_all).permute(0, 2, 1, 3).reshape(B, q, h * d)
+    assert present[0].shape == (B, h, kvl, d)
+    assert (ctx.float().cpu() - ref_ctx).abs().max().item() <= 2e-2
+    assert (probs.float().cpu().view(B, h, q, kvl) - p).abs().max().item() <= 2e-3

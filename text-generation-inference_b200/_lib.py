@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200_rope_kv_write_paged_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "b200_layernorm_residual": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _F, _P]),
     "b200_gelu": (_I, [_P, _P, _L, _I, _P]),
+    "b200_masked_softmax": (_I, [_P, _P, _P, _L, _L, _I, _P]),
     "b200_silu_mul": (_I, [_P, _P, _L, _L, _P]),
     "b200_embedding": (_I, [_P, _P, _P, _L, _L, _L, _L, _P]),
     "b200_argmax": (_I, [_P, _P, _L, _L, _L, _P, _P]),

@@ -328,6 +328,51 @@ __global__ void __launch_bounds__(kArgmaxThreads) argmax_kernel(const __half* __
 }
 
 // ------------------------------------------------------------------------------------------------
+// Masked softmax over rows of attention scores: the one CUDA kernel of the reference tree,
+// server/custom_kernels/custom_kernels/fused_attention_cuda.cu:28-107 (and its BLOOM twin): cast to fp32, positions with
+// mask != 0 are excluded, softmax over the rest in fp32, masked positions give 0, an all-masked row gives zeros (:95-99),
+// cast back.  One warp per row, 16-byte loads, shuffle reductions: no shared-memory atomics and no kv_length <= 4096 limit
+// (the reference needs kv / 4 <= 1024 threads, bloom_modeling.py:386-389).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) masked_softmax_kernel(const T* __restrict__ scores, const uint8_t* __restrict__ mask,
+                                                             T* __restrict__ out, int64_t rows, int64_t kv) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + warp_id();
+  if (row >= rows) return;
+  const T* sp = scores + row * kv;
+  const uint8_t* mp = mask + row * kv;
+  T* op = out + row * kv;
+  const int lane = lane_id();
+  float mx = -INFINITY;
+  for (int64_t i = lane; i < kv; i += 32)
+    if (mp[i] == 0) mx = fmaxf(mx, to_f32(sp[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int64_t i = lane; i < kv; i += 32)
+    if (mp[i] == 0) sum += expf(to_f32(sp[i]) - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int64_t i = lane; i < kv; i += 32)
+    op[i] = from_f32<T>((mp[i] == 0 && sum > 0.f) ? expf(to_f32(sp[i]) - mx) / sum : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // out[t, k'] = x[t, perm[k']]   (act-order GPTQ: activations follow the row order of the packed weight)
 // ------------------------------------------------------------------------------------------------
 __global__ void permute_columns_kernel(const __half* __restrict__ x, const int32_t* __restrict__ perm, __half* __restrict__ out,
@@ -429,6 +474,20 @@ extern "C" int b200_silu_mul(const void* gate_up, void* out, int64_t T, int64_t 
   int64_t blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   B200_LAUNCH(silu_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)gate_up, (__half*)out, I, total8);
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+extern "C" int b200_masked_softmax(const void* scores, const void* mask, void* out, int64_t rows, int64_t kv, int is_fp32, void* stream) {
+  if (rows == 0 || kv == 0) return B200_OK;
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+  if (is_fp32) {
+    B200_LAUNCH(masked_softmax_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const float*)scores, (const uint8_t*)mask,
+                (float*)out, rows, kv);
+  } else {
+    B200_LAUNCH(masked_softmax_kernel<__half>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)scores,
+                (const uint8_t*)mask, (__half*)out, rows, kv);
+  }
   b200_count_launches(1);
   return B200_OK;
 }

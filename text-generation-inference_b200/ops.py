@@ -62,6 +62,21 @@ def layernorm_residual(h: torch.Tensor, residual: Optional[torch.Tensor], gamma:
     return normed, (res_out if res_out is not None else h)
 
 
+def masked_softmax(scores: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Row softmax of `scores` [..., kv] (fp16 / fp32) over the positions where `mask` (bool, same shape) is False; the
+    forward_masked_softmax_kernel of server/custom_kernels (fp32 math, masked -> 0, all-masked row -> zeros)."""
+    if scores.dtype not in (torch.float16, torch.float32) or scores.device.type != "cuda":
+        raise _lib.B200Error("masked_softmax: need a CUDA fp16 or fp32 tensor")
+    assert mask.dtype == torch.bool and mask.shape == scores.shape
+    s2 = scores.contiguous()
+    m2 = mask.contiguous()
+    out = torch.empty_like(s2)
+    kv = s2.shape[-1]
+    _lib.check(_lib.load().b200_masked_softmax(_ptr(s2), _ptr(m2), _ptr(out), s2.numel() // max(kv, 1), kv,
+                                               int(scores.dtype == torch.float32), _stream()), "masked_softmax")
+    return out
+
+
 def gelu(x: torch.Tensor, approximate_tanh: bool = False) -> torch.Tensor:
     _req(x, torch.float16, "x")
     x = x.contiguous()
