@@ -7,32 +7,40 @@
 // utils/gptq/quant_linear.py:184-192:  W[k,n] = fp16( scales[g,n] * (q[k,n] - (qzeros[g,n] + 1)) ).
 //
 // Weight format.  `b200_gptq_pack` (the make_q_matrix analogue, once per linear at load time) turns the checkpoint
-// tensors into a stream of self-contained UNIT RECORDS, one per (128-feature tile, 128-wide k-block), tile-major:
+// tensors into a stream of self-contained UNIT RECORDS, one per (128-feature tile, 128-wide k-block):
 //     words  [4 chunks][128 features][4 x u32]   8 KB   chunk c = k 32c..32c+31 of the block; inside a word the 8 nibbles
 //                                                        are ordered k0 k2 k4 k6 | k1 k3 k5 k7 so one LOP3 yields a (k, k+1) pair
 //     meta   [group_rows][128 features] u32      512 B per row: fp16 scale | (zero + 1) << 16, group_rows = max(1, 128 / groupsize)
-// A CTA's work is a contiguous range of units == a contiguous byte range of HBM: one cp.async.bulk (TMA) per unit, no
-// tensor map, and the shared-memory image is exactly what the dequant threads want (LDS.128, conflict free).
+// ordered (super-tile = pair of feature tiles, k-block, tile of the pair).  A CTA's work is a contiguous range of
+// SUPER-UNITS (super-tile, k-block) == a contiguous byte range of HBM: one cp.async.bulk (TMA) per unit, no tensor map, and
+// the shared-memory image is exactly what the dequant threads want (LDS.128, conflict free).  The two units of a
+// super-unit share one activation tile (at T = 64 the activations are twice the weight bytes on the L2 -> SM path).
 //
-// Swap-AB like gemm_f16.cu: 128 output features = UMMA M, tokens = UMMA N (TN = 16..128), fp32 accumulator in TMEM.
-//   warp 0        TMA: unit records -> 16-deep (8 at TN = 128) weight ring.  Only these bytes come from HBM.
-//   warp 2        TMA: activations [TN x 128] fp16 as two 128B-swizzled sub-tiles -> 4-deep ring (L2 hits)
-//   warps 3..18   dequant: 4 teams x 4 warps; team = unit index mod 4, warp = TMEM lane quarter, thread = one feature row x
+// Swap-AB like gemm_f16.cu: 128 output features = UMMA M, tokens = UMMA N (TN = 16..128), fp32 accumulators in TMEM.
+// 24 warps, one CTA per SM.  The SM sub-partition arbiter favours high warp ids, so the pacing roles sit on top:
+//   warp 22       TMA: unit records -> 12..16-deep (8 at TN = 128) weight ring; starts before the CTA set-up barrier.
+//                 Only these bytes come from HBM.
+//   warp 23       TMA: one activation tile [TN x 128] fp16 (two 128B-swizzled sub-tiles) per super-unit -> 6-deep ring
+//                 (L2 hits); also watches the tiles land and counts them into s_ready
+//   warps 4..19   dequant: 4 teams x 4 warps; team = unit index mod 4, warp = TMEM lane quarter, thread = one feature row x
 //                 all 128 k of the unit (16 words).  Per 8 weights: 4 LOP3 + SHF (magic-number fp16: 1024 + q / 64 + q),
 //                 4 HADD2 (exact q - zero), 4 HMUL2 (x scale: bit-identical to the formula of record) -> tcgen05.st into a
-//                 ring of A-operand tiles in TMEM (64 columns each).  Teams run on their own clocks; nothing but
-//                 mbarriers couples them to the producers or the MMA warp.
-//   warp 1        one thread issues 8 x tcgen05.mma.kind::f16 per unit (A from TMEM, B from shared memory)
-//   warps 19..22  epilogue: tcgen05.ld of the finished accumulator (double buffered: the next tile's MMAs run meanwhile),
-//                 fp16 store, or fp32 partial store when the tile is shared with other CTAs
-// Decode (T <= 128) is weight-streaming / HBM-bound: the flattened (tile, k-block) unit space is cut into equal
-// contiguous ranges, one per SM (stream-K).  Tiles that straddle CTAs are finished after the main loop by ALL their
-// contributors: each sums one slice of the tile over the contributors' fp32 partials in contributor order
-// (deterministic, unlike the reference kernel's fp16 atomicAdd across K slices; a reduce-scatter, so the tail costs
-// one partial's worth of L2 reads per CTA however many CTAs share the tile).
+//                 ring of A-operand tiles in TMEM (64 columns each), counted into s_ready.  Teams run on their own clocks.
+//   warps 20, 21  MMA issue, alternate super-units: poll s_ready (one shared-memory word per super-unit), wait for the
+//                 turn (s_issued), 16 x tcgen05.mma.kind::f16 (A from TMEM, B from shared memory), ONE tcgen05.commit that
+//                 frees the activation stage and both A stages
+//   warps 0..3    epilogue: tcgen05.ld of a finished super-tile, then fp16 store / fused SiLU(gate) * up store / fp32
+//                 partial store when the super-tile is shared with other CTAs; they sleep while they wait
+// Decode (T <= 128) is weight-streaming / HBM-bound: the (super-tile, k-block) space is cut into contiguous ranges, one
+// per CTA, either equal shares of a super-tile or the balanced stream-K cut, whichever plan_w4's cost model prefers.
+// Super-tiles shared by several CTAs are finished after the main loop by ALL their contributors: each sums one slice over
+// the contributors' fp32 partials in contributor order (deterministic, unlike the reference kernel's fp16 atomicAdd across
+// K slices; a reduce-scatter, so the tail costs one partial's worth of L2 reads per CTA however many CTAs share it).
+// The contributors wait for one another: all CTAs of the grid are co-resident (grid <= #SMs, one CTA per SM).
 //
 // mbarrier rule used throughout: a thread that waits on a barrier observes every phase of it in order, or an earlier
-// observation implies the skipped phase completed (see the ring-depth static_asserts).
+// observation implies the skipped phase completed (see the ring-depth static_asserts).  Polls whose result is wanted
+// later use test_wait: try_wait may suspend the thread until a time-out while the phase is pending.
 #include "common.cuh"
 #include "tmap.cuh"
 
