@@ -95,3 +95,18 @@ def test_ops_fail_loudly_without_cuda(lib):
         ops.rmsnorm_residual(torch.zeros(2, 64, dtype=torch.float16), None, torch.ones(64, dtype=torch.float16), 1e-5)
     with pytest.raises(lib.B200Error):
         ops.gemm_f16(torch.zeros(2, 64, dtype=torch.float16), torch.zeros(8, 64, dtype=torch.float16))
+
+
+def test_gptq_packed_format_sizes(lib):
+    """host-side size rules of the int4 weight stream: 8 KB of words + 512 B of meta per group row for every
+    (128-feature tile, 128-wide k-block); feature tiles padded to pairs; k-blocks padded to a multiple of 8 when <= 5 %"""
+    h = lib.load()
+    rec = 8192 + 512
+    assert h.b200_gptq_packed_bytes(4096, 4096, 128) == 32 * 32 * rec
+    assert h.b200_gptq_packed_bytes(4096, 22016, 128) == 172 * 32 * rec
+    assert h.b200_gptq_packed_bytes(11008, 4096, 128) == 32 * 88 * rec          # 86 k-blocks -> 88
+    assert h.b200_gptq_packed_bytes(320, 288, 64) == 4 * 3 * (8192 + 2 * 512)   # 3 tiles -> 2 pairs; 2 meta rows
+    assert h.b200_gptq_packed_bytes(4096, 4096, -1) == 32 * 32 * rec            # one group: one meta row per record
+    assert h.b200_gptq_packed_bytes(4096, 4100, 128) < 0                        # N % 32 != 0 (exllamav2.py:118-119)
+    assert h.b200_gptq_packed_bytes(4096, 4096, 48) < 0                         # groupsize must divide / be divided by 128
+    assert b"groupsize" in h.b200_last_error()
