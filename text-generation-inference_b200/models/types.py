@@ -1,4 +1,8 @@
-"""`Batch` ABC and `GenerateError`.  Mirrors /root/reference/server/text_generation_server/models/types.py:15-62."""
+"""The batch contract between the shard server and a model (reference: models/types.py:15-62).
+
+`TextGenerationService` (server.py) keeps the objects returned by `from_pb` in its cache between calls and only ever touches
+them through this interface; `Model.generate_token` mutates them in place.
+"""
 from abc import ABC, abstractmethod
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
@@ -10,6 +14,7 @@ from .. import pb as generate_pb2
 
 @dataclass
 class GenerateError:
+    """A per-request failure that does not fail the whole batch (generate.proto:150-153)."""
     request_id: int
     message: str
 
@@ -18,29 +23,36 @@ class GenerateError:
 
 
 class Batch(ABC):
+    """What the server needs from a batch type; `FlashCausalLMBatch` is the one implementation on this path."""
+
     @abstractmethod
     def get_id(self) -> int:
+        """The router's batch id (cache key, cache.py:15-17)."""
         raise NotImplementedError
 
     @abstractmethod
     def __len__(self):
+        """Number of live requests."""
         raise NotImplementedError
 
     @classmethod
     @abstractmethod
-    def from_pb(cls, pb, tokenizer, dtype: torch.dtype, device: torch.device, embeddings_lookup: Optional,
-                prefix_cache: Optional, use_position_ids: bool = False) -> Tuple["Batch", List[GenerateError]]:
+    def from_pb(cls, pb, tokenizer, dtype: torch.dtype, device: torch.device, embeddings_lookup: Optional, prefix_cache: Optional,
+                use_position_ids: bool = False) -> Tuple["Batch", List[GenerateError]]:
+        """Tokenize a `generate.v1.Batch`; requests that fail validation come back as errors, not exceptions."""
         raise NotImplementedError
 
     @classmethod
     @abstractmethod
     def concatenate(cls, batches: List["Batch"]) -> "Batch":
+        """Merge cached batches after an add-on prefill (continuous batching); inputs must not be used afterwards."""
         raise NotImplementedError
 
     @classmethod
     @abstractmethod
     def prune(cls, batch: "Batch", completed_ids: List[int]) -> Optional["Batch"]:
+        """Drop finished requests; None when nothing is left, the same object when nothing finished."""
         raise NotImplementedError
 
     def compact(self):
-        pass
+        """Release slack memory before a new prefill (COMPACT_BEFORE_PREFILL, server.py:34); nothing to do for paged KV."""
