@@ -28,31 +28,26 @@ class Batch(ABC):
     @abstractmethod
     def get_id(self) -> int:
         """The router's batch id (cache key, cache.py:15-17)."""
-        raise NotImplementedError
 
     @abstractmethod
     def __len__(self):
         """Number of live requests."""
-        raise NotImplementedError
 
     @classmethod
     @abstractmethod
     def from_pb(cls, pb, tokenizer, dtype: torch.dtype, device: torch.device, embeddings_lookup: Optional, prefix_cache: Optional,
                 use_position_ids: bool = False) -> Tuple["Batch", List[GenerateError]]:
         """Tokenize a `generate.v1.Batch`; requests that fail validation come back as errors, not exceptions."""
-        raise NotImplementedError
 
     @classmethod
     @abstractmethod
     def concatenate(cls, batches: List["Batch"]) -> "Batch":
         """Merge cached batches after an add-on prefill (continuous batching); inputs must not be used afterwards."""
-        raise NotImplementedError
 
     @classmethod
     @abstractmethod
     def prune(cls, batch: "Batch", completed_ids: List[int]) -> Optional["Batch"]:
         """Drop finished requests; None when nothing is left, the same object when nothing finished."""
-        raise NotImplementedError
 
     def compact(self):
         """Release slack memory before a new prefill (COMPACT_BEFORE_PREFILL, server.py:34); nothing to do for paged KV."""
