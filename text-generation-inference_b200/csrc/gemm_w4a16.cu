@@ -133,6 +133,22 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// ---- thread-block cluster helpers (experimental DSMEM fix-up, B200_W4_CLUSTER=1)
+__device__ __forceinline__ uint32_t mapa_shared_cluster(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
 // non-blocking poll (mbarrier.try_wait may suspend the thread until a time-out when the phase is still pending)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -204,8 +220,10 @@ struct W4Params {
   unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
 };
 
-// kGR = meta rows per unit record (1, 2 or 4 = 128 / groupsize, 1 for groupsize >= 128)
-template <int TN, int kGR>
+// kGR = meta rows per unit record (1, 2 or 4 = 128 / groupsize, 1 for groupsize >= 128).
+// kCluster (experimental, off by default): the CTAs that share a super-tile form a thread-block cluster and exchange their
+// fp32 partials through distributed shared memory instead of the global workspace + counters.
+template <int TN, int kGR, bool kCluster>
 __global__ void __launch_bounds__(kW4Threads, 1)
 gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) {
   using C = GemmW4Cfg<TN>;
@@ -494,11 +512,21 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
           }
           tmem_ld_wait();
           if (!direct) {
+            if constexpr (kCluster) {
+              // stage the partial in this CTA's own shared memory (the weight ring is idle once the last accumulator is full)
+              const uint32_t stage = smem_u32(w_ring);
 #pragma unroll
-            for (int j = 0; j < kCh; ++j) {
-              if (t0 + c + j < p.T) {
-                part[(c + j) * kW4TileM + m] = __uint_as_float(d0[j]);
-                part[(TN + c + j) * kW4TileM + m] = __uint_as_float(d1[j]);
+              for (int j = 0; j < kCh; ++j) {
+                sts_f32(stage + (uint32_t)(((c + j) * kW4TileM + m) * 4), __uint_as_float(d0[j]));
+                sts_f32(stage + (uint32_t)(((TN + c + j) * kW4TileM + m) * 4), __uint_as_float(d1[j]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) {
+                if (t0 + c + j < p.T) {
+                  part[(c + j) * kW4TileM + m] = __uint_as_float(d0[j]);
+                  part[(TN + c + j) * kW4TileM + m] = __uint_as_float(d1[j]);
+                }
               }
             }
           } else if (p.act) {
@@ -527,10 +555,12 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
       W4_TRACE(9 + (seg & 3) * 2, 0);
       if (n_contrib > 1) {
         // release: the epilogue barrier orders every thread's partial stores before thread 0's gpu-scope fence + count
-        asm volatile("bar.sync 1, %0;" ::"n"(kW4EpWarps * 32) : "memory");
+        if constexpr (!kCluster) asm volatile("bar.sync 1, %0;" ::"n"(kW4EpWarps * 32) : "memory");
         if (threadIdx.x == 0) {
-          __threadfence();
-          atomicAdd(&p.counters[2 * tix], 1);
+          if constexpr (!kCluster) {
+            __threadfence();
+            atomicAdd(&p.counters[2 * tix], 1);
+          }
           s_fix[nfix][0] = tix;
           s_fix[nfix][1] = sup;
           s_fix[nfix][2] = n_contrib;
@@ -551,6 +581,58 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
   const int nfix = s_nfix;
   if (nfix > 0) pdl_wait();
   W4_TRACE(40, 0);
+  if constexpr (kCluster) {
+    // every CTA of the cluster shares this CTA's (only) super-tile: contributor index == rank in the cluster
+    static_assert(!kCluster || kW4R * TN * kW4TileM * 4 <= C::kWStages * kW4RecMaxBytes, "partial must fit in the weight ring");
+    cluster_sync_all();  // all partials are staged
+    if (nfix > 0) {
+      const int sup = s_fix[0][1], n_contrib = s_fix[0][2], my_contrib = s_fix[0][3];
+      const uint32_t stage = smem_u32(w_ring);
+      const int rows = min(p.T - t0, TN);
+      const int n_vec = p.act ? rows * (kW4TileM / 4) : kW4R * rows * (kW4TileM / 4);
+      const int per = (n_vec + n_contrib - 1) / n_contrib;
+      const int hi = min(n_vec, (my_contrib + 1) * per);
+      for (int idx = my_contrib * per + (int)threadIdx.x; idx < hi; idx += kW4Threads) {
+        const int r = p.act ? 0 : idx / (rows * (kW4TileM / 4));
+        const int rem = idx - r * rows * (kW4TileM / 4);
+        const int tt = rem / (kW4TileM / 4), mm = (rem % (kW4TileM / 4)) * 4;
+        const uint32_t off = (uint32_t)(((r * TN + tt) * kW4TileM + mm) * 4);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), u = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < n_contrib; ++c) {  // contributor order: deterministic
+          const float4 v = ld_dsmem_v4(mapa_shared_cluster(stage + off, (uint32_t)c));
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          if (p.act) {
+            const float4 w = ld_dsmem_v4(mapa_shared_cluster(stage + off + (uint32_t)(TN * kW4TileM * 4), (uint32_t)c));
+            u.x += w.x; u.y += w.y; u.z += w.z; u.w += w.w;
+          }
+        }
+        if (p.act) {
+          const int nn = sup * kW4TileM + mm, nu = nn + p.half_tiles * kW4TileM;
+          if (p.bias) {
+            a.x += __half2float(p.bias[nn]); a.y += __half2float(p.bias[nn + 1]); a.z += __half2float(p.bias[nn + 2]); a.w += __half2float(p.bias[nn + 3]);
+            u.x += __half2float(p.bias[nu]); u.y += __half2float(p.bias[nu + 1]); u.z += __half2float(p.bias[nu + 2]); u.w += __half2float(p.bias[nu + 3]);
+          }
+          __half o[4] = {silu_mul_f16(a.x, u.x), silu_mul_f16(a.y, u.y), silu_mul_f16(a.z, u.z), silu_mul_f16(a.w, u.w)};
+          *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.ldy + nn]) = *reinterpret_cast<uint2*>(o);
+        } else {
+          const int nn = (p.half_tiles ? sup + r * p.half_tiles : sup * kW4R + r) * kW4TileM + mm;
+          if (nn < p.N) {
+            if (p.bias) {
+              a.x += __half2float(p.bias[nn]); a.y += __half2float(p.bias[nn + 1]);
+              a.z += __half2float(p.bias[nn + 2]); a.w += __half2float(p.bias[nn + 3]);
+            }
+            uint2 o;
+            o.x = pack_half2(a.x, a.y);
+            o.y = pack_half2(a.z, a.w);
+            *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.ldy + nn]) = o;
+          }
+        }
+      }
+    }
+    cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
+    W4_TRACE(63, 0);
+    return;
+  }
   for (int f = 0; f < nfix; ++f) {
     const int tix = s_fix[f][0], sup = s_fix[f][1], n_contrib = s_fix[f][2], my_contrib = s_fix[f][3];
     if (threadIdx.x == 0) {
@@ -843,14 +925,28 @@ int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K) {
   return (int64_t)pl.n_tiles_t * pl.n_super * pl.max_contrib * kW4R * pl.TN * kW4TileM * 4;
 }
 
+// experimental: B200_W4_CLUSTER=1 runs aligned 2 / 4 / 8-way shared super-tiles as thread-block clusters (DSMEM fix-up)
+static bool w4_cluster_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_W4_CLUSTER");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int TN, int kGR>
 static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, void* workspace, const void* bias, int T, int N,
                           const W4Plan& pl, int half_tiles, int act, cudaStream_t st) {
   using C = GemmW4Cfg<TN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN, kGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN, kGR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
+    if constexpr (TN <= 64) {
+      e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN, kGR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+      if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
+    }
     configured = true;
   }
   W4Params p;
@@ -873,7 +969,31 @@ static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, vo
   p.trace = g_w4_trace;
   dim3 grid(pl.n_ctas, pl.n_tiles_t, 1);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 0, st);
-  B200_LAUNCH(gemm_w4a16_kernel<TN, kGR>, grid, dim3(kW4Threads), (size_t)C::kSmemBytes, st, *mx, p);
+  const int d = pl.su_per_cta > 0 ? pl.nkb / pl.su_per_cta : 0;  // CTAs per super-tile when the cut is aligned
+  bool clustered = false;
+  if constexpr (TN <= 64) {
+    if (w4_cluster_enabled() && pl.n_tiles_t == 1 && pl.max_contrib > 1 && pl.nkb % pl.su_per_cta == 0 && (d == 2 || d == 4 || d == 8) &&
+        pl.n_ctas == pl.n_super * d) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(kW4Threads);
+      cfg.dynamicSmemBytes = (size_t)C::kSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)d;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = b200_pdl_enabled() ? 2 : 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_w4a16_kernel<TN, kGR, true>, *mx, p);
+      if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
+      clustered = true;
+    }
+  }
+  if (!clustered) B200_LAUNCH(gemm_w4a16_kernel<TN, kGR, false>, grid, dim3(kW4Threads), (size_t)C::kSmemBytes, st, *mx, p);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 1, st);
   b200_count_launches(1);
   return B200_OK;
