@@ -94,8 +94,12 @@ def install_stubs():
     dln = types.ModuleType("dropout_layer_norm")
 
     def dropout_add_ln_fwd(x, residual, gamma, beta, rowscale, colscale, x0_subset, z_subset, p, eps, rs, zn, gen, res_fp32, is_rms):
-        assert is_rms and beta is None
-        normed, res = oll.rmsnorm_residual(x, residual, gamma, eps)
+        if is_rms:
+            assert beta is None
+            normed, res = oll.rmsnorm_residual(x, residual, gamma, eps)
+        else:  # LayerNorm mode (FastLayerNorm, utils/layers.py:376-392): the GPT-NeoX family
+            from oracle import neox as onx
+            normed, res = onx.layernorm_residual(x, residual, gamma, beta, eps)
         return normed, (res if residual is not None else None), None, None, None
     dln.dropout_add_ln_fwd = dropout_add_ln_fwd
     sys.modules["dropout_layer_norm"] = dln
@@ -295,6 +299,64 @@ def gold_flash_llama(layers, weights_mod, tmpdir):
     print("flash_llama_ref.npz", sorted(out)[:4], "...")
 
 
+def gold_flash_neox(layers, weights_mod, tmpdir):
+    """The reference's own FlashGPTNeoXForCausalLM (flash_neox_modeling.py) on CPU: prefill + 2 decode steps, both residual
+    forms -> flash_neox_ref.npz (graph wiring, QKV re-layout, partial rotary and KV handling pinned; the three CUDA
+    extensions are the oracle shims above)."""
+    from safetensors.torch import save_file
+    from oracle import neox as onx
+    fn = _load("text_generation_server.models.custom_modeling.flash_neox_modeling", "models/custom_modeling/flash_neox_modeling.py")
+    dist_mod = sys.modules.get("text_generation_server.utils.dist") or _load("text_generation_server.utils.dist", "utils/dist.py")
+    from transformers import GPTNeoXConfig
+    out = {}
+    for name, parallel in (("parallel", True), ("sequential", False)):
+        cfg = onx.NeoXConfig(128, 512, 2, 2, 160, rotary_pct=0.25, use_parallel_residual=parallel)
+        sd = onx.make_state_dict(cfg, seed=17, std=0.06)
+        path = os.path.join(tmpdir, f"neox_{name}.safetensors")
+        save_file({k: v.contiguous() for k, v in sd.items()}, path)
+        w = weights_mod.Weights([path], device="cpu", dtype=torch.float16, process_group=dist_mod.FakeGroup(0, 1))
+        hf = GPTNeoXConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                           num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads, rotary_pct=cfg.rotary_pct,
+                           rotary_emb_base=10000, layer_norm_eps=cfg.layer_norm_eps, use_parallel_residual=parallel, hidden_act="gelu")
+        hf.quantize = None
+        model = fn.FlashGPTNeoXForCausalLM(hf, w)
+        g = torch.Generator().manual_seed(9)
+        lens = [5, 12, 1]
+        prompts = [torch.randint(0, cfg.vocab_size, (L,), generator=g) for L in lens]
+        input_ids = torch.cat(prompts)
+        position_ids = torch.cat([torch.arange(L) for L in lens])
+        cu = torch.tensor([0, 5, 17, 18], dtype=torch.int32)
+        with torch.no_grad():
+            logits, present = model.forward(input_ids, position_ids, cu, None, max(lens), None, None, None)
+            out[f"{name}_prefill_logits"] = logits.numpy()
+            B = len(lens)
+            pad = present.new_zeros(present.shape[0], 1, *present.shape[2:])
+
+            def repad(present, cu):
+                pieces, start = [], 0
+                for i in range(1, B + 1):
+                    pieces += [present[:, start:int(cu[i])], pad]
+                    start = int(cu[i])
+                return torch.cat(pieces, dim=1)
+            past = repad(present, cu)
+            cu_q = torch.arange(B + 1, dtype=torch.int32)
+            nxt = logits[(cu[1:] - 1).long()].float().argmax(-1)
+            cu = cu + cu_q
+            pos = torch.tensor(lens)
+            for step in range(2):
+                out[f"{name}_decode{step}_input"] = nxt.numpy()
+                logits, present = model.forward(nxt, pos, cu, cu_q, max(lens) + 1 + step, None, past, None)
+                out[f"{name}_decode{step}_logits"] = logits.numpy()
+                past = repad(present, cu)
+                cu = cu + cu_q
+                pos = pos + 1
+                nxt = logits.float().argmax(-1)
+        out[f"{name}_input_ids"] = input_ids.numpy()
+        out[f"{name}_lens"] = np.array(lens)
+    np.savez(os.path.join(HERE, "flash_neox_ref.npz"), **out)
+    print("flash_neox_ref.npz", sorted(out)[:4], "...")
+
+
 def gold_proto():
     """field table of proto/generate.proto (message -> [name, number, type, label]) for tests/test_pb.py"""
     text = open("/root/reference/proto/generate.proto").read()
@@ -336,11 +398,19 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         gold_weights(weights_mod, tmp)
         gold_flash_llama(layers, weights_mod, tmp)
+        gold_flash_neox(layers, weights_mod, tmp)
     gold_chooser(my_pb)
     gold_batch(my_pb)
 
 
-if __name__ == "__main__" and "--batch-only" not in sys.argv:
+if __name__ == "__main__" and "--neox-only" in sys.argv:
+    import tempfile
+    install_stubs()
+    _layers = _load("text_generation_server.utils.layers", "utils/layers.py")
+    _weights = _load("text_generation_server.utils.weights", "utils/weights.py")
+    with tempfile.TemporaryDirectory() as _tmp:
+        gold_flash_neox(_layers, _weights, _tmp)
+elif __name__ == "__main__" and "--batch-only" not in sys.argv:
     main()
 
 
