@@ -10,11 +10,14 @@ What runs is reference code, imported from /root/reference/server/text_generatio
   utils/tokens.py + logits_process.py  HeterogeneousNextTokenChooser   -> chooser.npz
   models/custom_modeling/flash_llama_modeling.py  FlashLlamaForCausalLM.forward (prefill + decode, CPU fp16)
                                                                       -> flash_llama_ref.npz
+  models/custom_modeling/flash_neox_modeling.py   FlashGPTNeoXForCausalLM.forward (both residual forms; `--neox-only` regenerates
+                                                  just this one)      -> flash_neox_ref.npz
+  models/flash_causal_lm.py    FlashCausalLMBatch bookkeeping         -> batch_bookkeeping.npz
   proto/generate.proto (parsed, not executed)                         -> generate_proto_fields.json
 Stubs, and only these: modules that are absent from the image (`accelerate`, `loguru`-free paths, `rotary_emb`,
 `dropout_layer_norm`, `flash_attn_2_cuda`, the protoc-generated `pb.generate_pb2`) are replaced by thin shims; the
-three un-vendored CUDA kernels are shimmed with the oracle's restatement of their arithmetic (oracle/llama.py), so
-`flash_llama_ref.npz` pins the reference's *graph wiring, weight loading and KV handling* — its own Python — while the
+three un-vendored CUDA kernels are shimmed with the oracle's restatement of their arithmetic (oracle/llama.py, oracle/neox.py),
+so `flash_llama_ref.npz` / `flash_neox_ref.npz` pin the reference's *graph wiring, weight loading and KV handling* — its own Python — while the
 kernel arithmetic stays "parity unpinned" (SURVEY.md §8c).
 """
 from __future__ import annotations
