@@ -31,6 +31,7 @@ const char* b200_last_error(void);
 const char* b200_cuda_peek_error(void); /* debug: pending CUDA runtime error string, not cleared */
 void b200_debug_w4_flags(int flags); /* debug timing experiments (results invalid): 1 no x loads, 2 no MMAs, 4 no weight loads, 8 no dequant math */
 void b200_debug_w4_trace(void* device_buffer); /* debug: [n_ctas][64] u64 phase timestamps of int4 GEMM launches; NULL = off */
+int b200_debug_gemm_plan(int kind, int64_t T, int64_t N, int64_t K, int sms, int32_t* out8); /* tests, host only: stream-K plan of a launch; kind 0 fp16, 1 int4; out = {token tile, k-blocks, feature (super-)tiles, token tiles, units per CTA, CTAs, contributor slots, tiles per unit} */
 /* number of kernels this library has enqueued in this process (bench.py reports the delta as "gpu_launches") */
 int64_t b200_launch_count(void);
 

@@ -17,6 +17,7 @@ SIGNATURES = {
     "b200_cuda_peek_error": (c_char_p, []),
     "b200_debug_w4_trace": (None, [_P]),
     "b200_debug_w4_flags": (None, [_I]),
+    "b200_debug_gemm_plan": (_I, [_I, _L, _L, _L, _I, _P]),
     "b200_rmsnorm_residual": (_I, [_P, _P, _P, _P, _P, _L, _L, _F, _P]),
     "b200_rope_kv_write_paged": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     "b200_rope_kv_write_paged_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),

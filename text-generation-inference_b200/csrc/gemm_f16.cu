@@ -313,6 +313,25 @@ static F16Plan plan_f16(int64_t T, int64_t N, int64_t K, int sms) {
 using namespace b200;
 
 int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K);  // gemm_w4a16.cu (stream-K partials)
+void b200_w4_plan_debug(int64_t T, int64_t N, int64_t K, int sms, int32_t* out);
+
+// tests (no GPU needed): the stream-K plan of one GEMM launch.  kind 0 = fp16 weights, 1 = int4.
+// out[8] = {token tile, k-blocks per tile, feature tiles (int4: super-tiles), token tiles, units per CTA, CTAs,
+//           contributor slots per tile in the workspace, feature tiles per unit (int4: 2)}
+extern "C" int b200_debug_gemm_plan(int kind, int64_t T, int64_t N, int64_t K, int sms, int32_t* out) {
+  if (!out || T <= 0 || N <= 0 || K <= 0 || sms <= 0 || (kind != 0 && kind != 1)) {
+    b200_set_last_error("debug_gemm_plan: bad arguments");
+    return B200_ERR_ARG;
+  }
+  if (kind == 1) {
+    b200_w4_plan_debug(T, N, K, sms, out);
+    return B200_OK;
+  }
+  const F16Plan pl = plan_f16(T, N, K, sms);
+  const int32_t v[8] = {pl.TN, pl.nkb, pl.n_tiles_n, pl.n_tiles_t, pl.units_per_cta, pl.n_ctas, pl.max_contrib, 1};
+  for (int i = 0; i < 8; ++i) out[i] = v[i];
+  return B200_OK;
+}
 
 extern "C" int64_t b200_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K) {
   const F16Plan pl = plan_f16(T, N, K, 148);

@@ -919,6 +919,25 @@ extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const voi
 }
 
 // bytes of split-K partials the int4 GEMM may write for this shape (the tile counters sit in the first 64 KiB)
+// The plan a launch uses: the stream-K cut needs the workspace (partials + one counter pair per super-tile) and every CTA
+// resident at once (the fix-up spins on its peers); otherwise each CTA takes whole super-tiles.
+static W4Plan launch_plan_w4(int64_t T, int64_t N, int64_t K, int sms, bool has_workspace) {
+  W4Plan pl = plan_w4(T, N, K, sms);
+  if (pl.max_contrib > 1 && (!has_workspace || (int64_t)pl.n_super * pl.n_tiles_t * 8 > kW4CounterBytes || pl.n_ctas > sms)) {
+    pl.su_per_cta = pl.nkb;
+    pl.n_ctas = pl.n_super;
+    pl.max_contrib = 1;
+  }
+  return pl;
+}
+
+// tests (no GPU needed): out = {TN, k-blocks, super-tiles, token tiles, super-units per CTA, CTAs, contributor slots, R}
+void b200_w4_plan_debug(int64_t T, int64_t N, int64_t K, int sms, int32_t* out) {
+  const W4Plan pl = launch_plan_w4(T, N, K, sms, true);
+  const int32_t v[8] = {pl.TN, pl.nkb, pl.n_super, pl.n_tiles_t, pl.su_per_cta, pl.n_ctas, pl.max_contrib, kW4R};
+  for (int i = 0; i < 8; ++i) out[i] = v[i];
+}
+
 int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K) {
   const W4Plan pl = plan_w4(T, N, K, num_sms());
   if (pl.max_contrib <= 1) return 0;
@@ -1011,12 +1030,7 @@ extern "C" int b200_gemm_w4a16_ex(const void* x, const void* packed, const void*
   if (half_tiles < 0) return B200_ERR_ARG;
   if (act != 0 && (act != 1 || layout != 1)) { b200_set_last_error("gemm_w4a16: act = 1 needs the gate|up layout"); return B200_ERR_ARG; }
   const int gr = w4_group_rows(K, &groupsize);
-  W4Plan pl = plan_w4(T, N, K, num_sms());
-  if (pl.max_contrib > 1 && (!workspace || (int64_t)pl.n_super * pl.n_tiles_t * 8 > kW4CounterBytes || pl.n_ctas > num_sms())) {
-    pl.su_per_cta = pl.nkb;  // whole super-tiles per CTA
-    pl.n_ctas = pl.n_super;
-    pl.max_contrib = 1;
-  }
+  const W4Plan pl = launch_plan_w4(T, N, K, num_sms(), workspace != nullptr);
   const CUtensorMap* mx = get_tmap_2d(x, T, K, K, pl.TN, 64, TmapDtype::kF16, TmapSwizzle::k128B);
   if (!mx) return B200_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
