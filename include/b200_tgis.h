@@ -177,6 +177,16 @@ int b200_decode_advance(const int32_t* block_table, int64_t block_table_stride, 
  * One call enqueues a whole prefill / decode step of the Llama graph; replaces the Python op sequence of
  * FlashLlamaForCausalLM.forward (models/custom_modeling/flash_llama_modeling.py:425-540).  All pointers device
  * memory owned by the caller (weights: the model; scratch: the host runtime). */
+/* ---- one-shot all-reduce over NVLink peer memory (EXPERIMENTAL; replaces torch.distributed.all_reduce at the tensor-parallel
+ * layer boundary, utils/layers.py:303-306, :343-345, for decode-sized messages).  create -> exchange the IPC handles of all
+ * ranks (any transport) -> connect -> allreduce (CUDA-graph capturable; every rank must issue the same calls). */
+int b200_p2p_handle_bytes(void);
+int b200_p2p_create(int64_t max_bytes, int world, int rank, void** ctx_out, void* handle_out);
+int b200_p2p_connect(void* ctx, const void* handles /* [world][b200_p2p_handle_bytes()] */);
+int64_t b200_p2p_max_bytes(void* ctx);
+int b200_p2p_allreduce_f16(void* ctx, void* data /* fp16 [n], in place, sums in rank order with fp32 accumulation */, int64_t n, void* stream);
+void b200_p2p_destroy(void* ctx);
+
 typedef struct {
   const void* weight;  /* fp16 [N, K], or NULL when GPTQ */
   const void* qweight; /* GPTQ: the b200_gptq_pack output for this linear, or NULL */

@@ -110,3 +110,25 @@ def test_gptq_packed_format_sizes(lib):
     assert h.b200_gptq_packed_bytes(4096, 4100, 128) < 0                        # N % 32 != 0 (exllamav2.py:118-119)
     assert h.b200_gptq_packed_bytes(4096, 4096, 48) < 0                         # groupsize must divide / be divided by 128
     assert b"groupsize" in h.b200_last_error()
+
+
+def test_p2p_allreduce_argument_checks(lib):
+    """the peer-memory all-reduce (experimental) validates before it touches CUDA, and has no CPU form"""
+    import torch
+    h = lib.load()
+    assert h.b200_p2p_handle_bytes() == 64  # cudaIpcMemHandle_t
+    ctx = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    assert h.b200_p2p_create(1 << 20, 1, 0, ctypes.byref(ctx), handle) != 0   # a group of one has nothing to reduce
+    assert h.b200_p2p_create(1 << 20, 9, 0, ctypes.byref(ctx), handle) != 0   # one NVSwitch domain: <= 8 ranks
+    assert h.b200_p2p_create(1 << 20, 2, 2, ctypes.byref(ctx), handle) != 0
+    assert h.b200_p2p_allreduce_f16(None, None, 8, None) != 0
+    assert h.b200_p2p_max_bytes(None) == 0
+    if not torch.cuda.is_available():
+        assert h.b200_p2p_create(1 << 20, 2, 0, ctypes.byref(ctx), handle) != 0  # no device: fails loudly
+    # default: NCCL / gloo stays the transport unless B200_P2P_ALLREDUCE=1
+    from tgis_b200.utils.dist import FakeGroup
+    from tgis_b200.utils.p2p import LayerBoundaryAllReduce
+    reduce = LayerBoundaryAllReduce(FakeGroup(0, 1))
+    x = torch.ones(8, dtype=torch.float16)
+    assert not reduce.uses_peer_memory and reduce(x) is x

@@ -17,6 +17,7 @@ SWITCHES = [
     ("B200_ATTN_PERSISTENT", "tests/test_gpu_ops.py::test_attn_decode_paged"),  # persistent split-KV decode attention
     ("B200_W4_CLUSTER", "tests/test_gpu_gemm.py"),                                # int4 GEMM: stream-K fix-up over DSMEM
     ("B200_F16_ALIGNED", "tests/test_gpu_gemm.py"),                               # fp16 GEMM: aligned stream-K cuts
+    ("B200_P2P_ALLREDUCE", "tests/test_gpu_tp.py"),                               # TP boundary over NVLink peer memory (2 GPUs)
 ]
 
 

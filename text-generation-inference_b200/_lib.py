@@ -38,6 +38,12 @@ SIGNATURES = {
     "b200_gemm_workspace_bytes": (_L, [_L, _L, _L]),
     "b200_gemm_workspace_bytes_max": (_L, [_L, _L]),
     "b200_gemm_f16": (_I, [_P, _P, _P, _P, _L, _L, _L, _P, _P]),
+    "b200_p2p_handle_bytes": (_I, []),
+    "b200_p2p_create": (_I, [_L, _I, _I, ctypes.POINTER(_P), _P]),
+    "b200_p2p_connect": (_I, [_P, _P]),
+    "b200_p2p_max_bytes": (_L, [_P]),
+    "b200_p2p_allreduce_f16": (_I, [_P, _P, _L, _P]),
+    "b200_p2p_destroy": (None, [_P]),
     "b200_gptq_packed_bytes": (_L, [_L, _L, _I]),
     "b200_gptq_pack": (_I, [_P, _P, _P, _P, _L, _L, _I, _P]),
     "b200_gptq_pack_ex": (_I, [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P]),

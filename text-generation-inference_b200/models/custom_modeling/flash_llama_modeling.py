@@ -30,6 +30,7 @@ from ...utils.layers import (
     TensorParallelRowLinear,
 )
 from ...utils.gptq.exllamav2 import Ex4bitLinearV2
+from ...utils.p2p import LayerBoundaryAllReduce
 from ...utils.paged import PagedKVCacheManager, PagedKVState
 
 
@@ -188,6 +189,7 @@ class FlashLlamaForCausalLM(nn.Module):
         self.kv_cache_manager: Optional[PagedKVCacheManager] = None
         self._cw = None
         self.scratch = StepScratch(self)
+        self._all_reduce = LayerBoundaryAllReduce(self.process_group)  # NCCL unless B200_P2P_ALLREDUCE=1 (utils/p2p.py)
 
     def get_input_embeddings(self) -> nn.Module:
         return self.model.embed_tokens
@@ -284,14 +286,14 @@ class FlashLlamaForCausalLM(nn.Module):
         if embed:
             _lib.check(lib.b200_llama_embed(ctypes.byref(w), ctypes.byref(s), st), "llama_embed")
             if tp > 1:
-                torch.distributed.all_reduce(hidden, group=self.process_group)
+                self._all_reduce(hidden)
         for l in range(w.n_layers):
             _lib.check(lib.b200_llama_attn_block(ctypes.byref(w), ctypes.byref(s), l, st), "llama_attn_block")
             if tp > 1:
-                torch.distributed.all_reduce(hidden, group=self.process_group)
+                self._all_reduce(hidden)
             _lib.check(lib.b200_llama_mlp_block(ctypes.byref(w), ctypes.byref(s), l, st), "llama_mlp_block")
             if tp > 1:
-                torch.distributed.all_reduce(hidden, group=self.process_group)
+                self._all_reduce(hidden)
         _lib.check(lib.b200_llama_head(ctypes.byref(w), ctypes.byref(s), st), "llama_head")
 
     # ---------------------------------------------------------------------------- reference-shaped forward
