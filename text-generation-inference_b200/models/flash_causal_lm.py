@@ -277,7 +277,8 @@ class FlashCausalLM(Model):
     def _can_fuse_greedy(self, batch) -> bool:
         """All-greedy batch with no per-token details on a single rank: arg-max (with the min_new_tokens EOS mask)
         runs inside the step and the ids chain device-to-device; the host reads back B ids per step."""
-        if not hasattr(self.model, "make_step"):  # families without the C++ step runtime (flash GPT-NeoX) run op by op
+        # families without the C++ step runtime (flash GPT-NeoX) run op by op unless their Python step is switched on
+        if not getattr(self.model, "fused_greedy_enabled", hasattr(self.model, "make_step")):
             return False
         if not batch.next_token_chooser.is_plain_greedy:
             return False
@@ -300,6 +301,8 @@ class FlashCausalLM(Model):
                                               position_ids=batch.position_ids, kv=kv, logits=st["logits"],
                                               next_ids=st["next_ids"] if tp == 1 else None)
             st["step"].banned_ids = st["banned"].data_ptr()
+            if hasattr(st["step"], "banned"):  # Python step objects (NeoxStep) take the tensor itself
+                st["step"].banned = st["banned"]
             if tp > 1 and self.model.lm_head.should_gather:
                 # vocab-sharded head: all-gather the [B, V/tp] logits (utils/layers.py:249-269), then one arg-max
                 st["gathered"] = torch.empty(tp, B, V, dtype=torch.float16, device=self.device)
