@@ -88,8 +88,10 @@ class HeterogeneousTopKLogitsWarper:
 
     def __call__(self, input_ids, scores):
         if scores.size(-1) < self.max_top_k:
+            # the reference clamps the 0-based index to V (logits_process.py:280-282) and then indexes out of bounds for
+            # k > V; V - 1 is what its comment intends ("clamp or the warper will fail")
             max_top_k = scores.size(-1)
-            top_k = torch.clamp_max(self.top_k_tensor, max_top_k)
+            top_k = torch.clamp_max(self.top_k_tensor, max_top_k - 1)
         else:
             max_top_k, top_k = self.max_top_k, self.top_k_tensor
         kth = torch.gather(torch.topk(scores, max_top_k).values, 1, top_k)
