@@ -177,7 +177,10 @@ def _tp_worker(rank, world, port, path, quant, out_q):
     ok = (local >= 0) & (local < block)
     e = torch.zeros(4, cfg.hidden_size)
     e[ok] = emb[local[ok]].float()
-    dist.all_reduce(e)
+    from tgis_b200.utils.p2p import LayerBoundaryAllReduce
+    reduce = LayerBoundaryAllReduce(pg)                    # what FlashLlama's step calls at the layer boundary
+    assert not reduce.uses_peer_memory                     # the peer-memory kernel is opt-in and GPU-only: gloo here
+    assert reduce(e) is e
     if rank == 0:
         out_q.put((part, e))
     dist.barrier()
