@@ -360,6 +360,64 @@ def gold_flash_neox(layers, weights_mod, tmpdir):
     print("flash_neox_ref.npz", sorted(out)[:4], "...")
 
 
+def gold_flash_santacoder(layers, weights_mod, tmpdir):
+    """The reference's own FlashSantacoderForCausalLM (flash_santacoder_modeling.py, multi-query attention) on CPU: prefill + 2
+    decode steps -> flash_santacoder_ref.npz (c_attn q | kv split, learned positions, KV placement, sequential residual,
+    tied head pinned; LayerNorm and attention are the oracle shims above)."""
+    from safetensors.torch import save_file
+    from oracle import santacoder as osc
+    fs = _load("text_generation_server.models.custom_modeling.flash_santacoder_modeling",
+               "models/custom_modeling/flash_santacoder_modeling.py")
+    dist_mod = sys.modules.get("text_generation_server.utils.dist") or _load("text_generation_server.utils.dist", "utils/dist.py")
+    from transformers import GPTBigCodeConfig
+    cfg = osc.SantacoderConfig(128, 512, 2, 4, 160, n_positions=64)
+    sd = osc.make_state_dict(cfg, seed=23, std=0.06)
+    path = os.path.join(tmpdir, "santacoder.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    w = weights_mod.Weights([path], device="cpu", dtype=torch.float16, process_group=dist_mod.FakeGroup(0, 1))
+    hf = GPTBigCodeConfig(vocab_size=cfg.vocab_size, n_positions=cfg.n_positions, n_embd=cfg.hidden_size, n_layer=cfg.num_hidden_layers,
+                          n_head=cfg.num_attention_heads, n_inner=cfg.n_inner, activation_function=cfg.activation_function,
+                          layer_norm_epsilon=cfg.layer_norm_epsilon, multi_query=True)
+    hf.quantize, hf.transpose = None, False  # tgis_native.py:84: transpose only for GPT2-architecture checkpoints
+    model = fs.FlashSantacoderForCausalLM(hf, w)
+    g = torch.Generator().manual_seed(13)
+    lens = [6, 11, 2]
+    prompts = [torch.randint(0, cfg.vocab_size, (L,), generator=g) for L in lens]
+    input_ids = torch.cat(prompts)
+    position_ids = torch.cat([torch.arange(L) for L in lens])
+    cu = torch.tensor([0, 6, 17, 19], dtype=torch.int32)
+    out = {}
+    with torch.no_grad():
+        logits, present = model.forward(input_ids, position_ids, cu, None, max(lens), None, None, None)
+        out["prefill_logits"] = logits.numpy()
+        B = len(lens)
+        pad = present.new_zeros(present.shape[0], 1, *present.shape[2:])
+
+        def repad(present, cu):
+            pieces, start = [], 0
+            for i in range(1, B + 1):
+                pieces += [present[:, start:int(cu[i])], pad]
+                start = int(cu[i])
+            return torch.cat(pieces, dim=1)
+        past = repad(present, cu)
+        cu_q = torch.arange(B + 1, dtype=torch.int32)
+        nxt = logits[(cu[1:] - 1).long()].float().argmax(-1)
+        cu = cu + cu_q
+        pos = torch.tensor(lens)
+        for step in range(2):
+            out[f"decode{step}_input"] = nxt.numpy()
+            logits, present = model.forward(nxt, pos, cu, cu_q, max(lens) + 1 + step, None, past, None)
+            out[f"decode{step}_logits"] = logits.numpy()
+            past = repad(present, cu)
+            cu = cu + cu_q
+            pos = pos + 1
+            nxt = logits.float().argmax(-1)
+    out["input_ids"] = input_ids.numpy()
+    out["lens"] = np.array(lens)
+    np.savez(os.path.join(HERE, "flash_santacoder_ref.npz"), **out)
+    print("flash_santacoder_ref.npz", sorted(out)[:4], "...")
+
+
 def gold_proto():
     """field table of proto/generate.proto (message -> [name, number, type, label]) for tests/test_pb.py"""
     text = open("/root/reference/proto/generate.proto").read()
@@ -402,6 +460,7 @@ def main():
         gold_weights(weights_mod, tmp)
         gold_flash_llama(layers, weights_mod, tmp)
         gold_flash_neox(layers, weights_mod, tmp)
+        gold_flash_santacoder(layers, weights_mod, tmp)
     gold_chooser(my_pb)
     gold_batch(my_pb)
 
@@ -413,6 +472,13 @@ if __name__ == "__main__" and "--neox-only" in sys.argv:
     _weights = _load("text_generation_server.utils.weights", "utils/weights.py")
     with tempfile.TemporaryDirectory() as _tmp:
         gold_flash_neox(_layers, _weights, _tmp)
+elif __name__ == "__main__" and "--santacoder-only" in sys.argv:
+    import tempfile
+    install_stubs()
+    _layers = _load("text_generation_server.utils.layers", "utils/layers.py")
+    _weights = _load("text_generation_server.utils.weights", "utils/weights.py")
+    with tempfile.TemporaryDirectory() as _tmp:
+        gold_flash_santacoder(_layers, _weights, _tmp)
 elif __name__ == "__main__" and "--batch-only" not in sys.argv:
     main()
 
