@@ -3,7 +3,8 @@ process group, opens the safetensors shards with the TP slicing rules and builds
 
 Mirrors /root/reference/server/text_generation_server/inference_engine/engine.py:11-37 (`BaseInferenceEngine`:
 config/tokenizer loading, RANK / WORLD_SIZE, device = rank % device_count) and inference_engine/tgis_native.py:24-139.
-Only the flash decoder families of the hot path exist here (llama, gpt_neox); other model types raise NotImplementedError.
+Only the flash decoder families of the hot path exist here (llama, gpt_neox, and - experimental - gpt_bigcode); other model
+types raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ import torch.distributed
 from .utils.dist import initialize_torch_distributed
 from .utils.weights import Weights
 
-FLASH_TYPES = ["llama", "gpt_neox"]
+FLASH_TYPES = ["llama", "gpt_neox", "gpt_bigcode"]
 
 
 def local_weight_files(model_path: str, extension: str = ".safetensors"):
@@ -57,6 +58,13 @@ class InferenceEngine:
         elif model_type == "gpt_neox":  # tgis_native.py:75-79
             from .models.custom_modeling.flash_neox_modeling import FlashGPTNeoXForCausalLM
             model_class = FlashGPTNeoXForCausalLM
+        elif model_type == "gpt_bigcode":  # tgis_native.py:83-92
+            archs = getattr(self._config, "architectures", None) or [""]
+            self._config.transpose = archs[0].startswith("GPT2")
+            if not getattr(self._config, "multi_query", True):
+                raise NotImplementedError("gpt_bigcode without multi_query is not a flash santacoder model")
+            from .models.custom_modeling.flash_santacoder_modeling import FlashSantacoderForCausalLM
+            model_class = FlashSantacoderForCausalLM
         self._config.quantize = quantize
         self.process_group = initialize_torch_distributed(self.world_size, self.rank)
         self.master = self.rank == 0
