@@ -418,6 +418,69 @@ def gold_flash_santacoder(layers, weights_mod, tmpdir):
     print("flash_santacoder_ref.npz", sorted(out)[:4], "...")
 
 
+FALCON_CASES = {  # name -> (hidden, layers, heads, kv heads, vocab, new_decoder_architecture, parallel_attn, bias)
+    "mqa_parallel": (128, 2, 4, 1, 160, False, True, False),
+    "gqa_large": (256, 2, 8, 2, 160, True, True, False),
+    "mqa_sequential_bias": (128, 2, 2, 1, 160, False, False, True),
+}
+
+
+def gold_flash_rw(layers, weights_mod, tmpdir):
+    """The reference's own FlashRWForCausalLM (flash_rw_modeling.py: Falcon / RefinedWeb) on CPU in its three layer forms:
+    prefill + 2 decode steps -> flash_rw_ref.npz (fused-QKV layouts, rotary on q and k, KV placement, parallel / sequential /
+    two-LayerNorm residual wiring pinned; LayerNorm, rotary and attention are the oracle shims above)."""
+    from safetensors.torch import save_file
+    from oracle import falcon as ofa
+    fr = _load("text_generation_server.models.custom_modeling.flash_rw_modeling", "models/custom_modeling/flash_rw_modeling.py")
+    dist_mod = sys.modules.get("text_generation_server.utils.dist") or _load("text_generation_server.utils.dist", "utils/dist.py")
+    out = {}
+    for name, (H, L, h, kvh, V, large, parallel, bias) in FALCON_CASES.items():
+        cfg = ofa.FalconConfig(H, L, h, kvh, V, new_decoder_architecture=large, parallel_attn=parallel, bias=bias)
+        sd = ofa.make_state_dict(cfg, seed=29, std=0.06)
+        path = os.path.join(tmpdir, f"falcon_{name}.safetensors")
+        save_file({k: v.contiguous() for k, v in sd.items()}, path)
+        w = weights_mod.Weights([path], device="cpu", dtype=torch.float16, process_group=dist_mod.FakeGroup(0, 1))
+        rw = fr.RWConfig(model_type="RefinedWeb" if large else "RefinedWebModel", vocab_size=V, hidden_size=H, num_hidden_layers=L,
+                         num_attention_heads=h, num_kv_heads=kvh, new_decoder_architecture=large, bias=bias, parallel_attn=parallel)
+        rw.quantize = None
+        model = fr.FlashRWForCausalLM(rw, w)
+        g = torch.Generator().manual_seed(15)
+        lens = [4, 13, 2]
+        prompts = [torch.randint(0, V, (n,), generator=g) for n in lens]
+        input_ids = torch.cat(prompts)
+        position_ids = torch.cat([torch.arange(n) for n in lens])
+        cu = torch.tensor([0, 4, 17, 19], dtype=torch.int32)
+        with torch.no_grad():
+            logits, present = model.forward(input_ids, position_ids, cu, None, max(lens), None, None, None)
+            out[f"{name}_prefill_logits"] = logits.numpy()
+            B = len(lens)
+            pad = present.new_zeros(present.shape[0], 1, *present.shape[2:])
+
+            def repad(present, cu):
+                pieces, start = [], 0
+                for i in range(1, B + 1):
+                    pieces += [present[:, start:int(cu[i])], pad]
+                    start = int(cu[i])
+                return torch.cat(pieces, dim=1)
+            past = repad(present, cu)
+            cu_q = torch.arange(B + 1, dtype=torch.int32)
+            nxt = logits[(cu[1:] - 1).long()].float().argmax(-1)
+            cu = cu + cu_q
+            pos = torch.tensor(lens)
+            for step in range(2):
+                out[f"{name}_decode{step}_input"] = nxt.numpy()
+                logits, present = model.forward(nxt, pos, cu, cu_q, max(lens) + 1 + step, None, past, None)
+                out[f"{name}_decode{step}_logits"] = logits.numpy()
+                past = repad(present, cu)
+                cu = cu + cu_q
+                pos = pos + 1
+                nxt = logits.float().argmax(-1)
+        out[f"{name}_input_ids"] = input_ids.numpy()
+        out[f"{name}_lens"] = np.array(lens)
+    np.savez(os.path.join(HERE, "flash_rw_ref.npz"), **out)
+    print("flash_rw_ref.npz", sorted(out)[:4], "...")
+
+
 def gold_proto():
     """field table of proto/generate.proto (message -> [name, number, type, label]) for tests/test_pb.py"""
     text = open("/root/reference/proto/generate.proto").read()
@@ -461,6 +524,7 @@ def main():
         gold_flash_llama(layers, weights_mod, tmp)
         gold_flash_neox(layers, weights_mod, tmp)
         gold_flash_santacoder(layers, weights_mod, tmp)
+        gold_flash_rw(layers, weights_mod, tmp)
     gold_chooser(my_pb)
     gold_batch(my_pb)
 
@@ -472,6 +536,13 @@ if __name__ == "__main__" and "--neox-only" in sys.argv:
     _weights = _load("text_generation_server.utils.weights", "utils/weights.py")
     with tempfile.TemporaryDirectory() as _tmp:
         gold_flash_neox(_layers, _weights, _tmp)
+elif __name__ == "__main__" and "--falcon-only" in sys.argv:
+    import tempfile
+    install_stubs()
+    _layers = _load("text_generation_server.utils.layers", "utils/layers.py")
+    _weights = _load("text_generation_server.utils.weights", "utils/weights.py")
+    with tempfile.TemporaryDirectory() as _tmp:
+        gold_flash_rw(_layers, _weights, _tmp)
 elif __name__ == "__main__" and "--santacoder-only" in sys.argv:
     import tempfile
     install_stubs()
