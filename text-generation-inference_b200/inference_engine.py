@@ -3,7 +3,7 @@ process group, opens the safetensors shards with the TP slicing rules and builds
 
 Mirrors /root/reference/server/text_generation_server/inference_engine/engine.py:11-37 (`BaseInferenceEngine`:
 config/tokenizer loading, RANK / WORLD_SIZE, device = rank % device_count) and inference_engine/tgis_native.py:24-139.
-Only the flash decoder families of the hot path exist here (llama, gpt_neox, and - experimental - gpt_bigcode); other model
+Only the flash decoder families of the hot path exist here (llama, gpt_neox, and - experimental - gpt_bigcode and falcon / RefinedWeb); other model
 types raise NotImplementedError.
 """
 from __future__ import annotations
@@ -18,7 +18,7 @@ import torch.distributed
 from .utils.dist import initialize_torch_distributed
 from .utils.weights import Weights
 
-FLASH_TYPES = ["llama", "gpt_neox", "gpt_bigcode"]
+FLASH_TYPES = ["llama", "gpt_neox", "gpt_bigcode", "falcon", "RefinedWeb", "RefinedWebModel"]
 
 
 def local_weight_files(model_path: str, extension: str = ".safetensors"):
@@ -65,6 +65,11 @@ class InferenceEngine:
                 raise NotImplementedError("gpt_bigcode without multi_query is not a flash santacoder model")
             from .models.custom_modeling.flash_santacoder_modeling import FlashSantacoderForCausalLM
             model_class = FlashSantacoderForCausalLM
+        elif model_type in ("falcon", "RefinedWeb", "RefinedWebModel"):  # tgis_native.py:59-73
+            if getattr(self._config, "alibi", False):
+                raise NotImplementedError("alibi is not supported by this version of the model")
+            from .models.custom_modeling.flash_rw_modeling import FlashRWForCausalLM
+            model_class = FlashRWForCausalLM
         self._config.quantize = quantize
         self.process_group = initialize_torch_distributed(self.world_size, self.rank)
         self.master = self.rank == 0

@@ -219,6 +219,11 @@ class FlashSantacoderForCausalLM(nn.Module):
         self.lm_head = TensorParallelHead.load(config, prefix="transformer.wte", weights=weights)  # tied to the embedding (:447-449)
         self.max_positions = int(getattr(config, "n_positions", 0) or getattr(config, "max_position_embeddings", 2048) or 2048)
 
+    @staticmethod
+    def kv_cache_layout(config, world: int):
+        """(KV heads in the whole model, ranks they are split over): one head, kept whole on every rank (:214-224)"""
+        return 1, 1
+
     # the attributes FlashCausalLM / the server read on a flash model
     @property
     def model(self):

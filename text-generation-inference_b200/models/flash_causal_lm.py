@@ -217,8 +217,9 @@ class FlashCausalLM(Model):
             num_kv_blocks = int(os.environ["KV_CACHE_MANAGER_NUM_GPU_BLOCKS"])  # paged_causal_lm.py:310-311
         world = getattr(engine, "world_size", 1)
         kv_heads, kv_world = getattr(cfg, "num_key_value_heads", None) or cfg.num_attention_heads, world
-        if getattr(cfg, "model_type", None) == "gpt_bigcode" and getattr(cfg, "multi_query", True):
-            kv_heads, kv_world = 1, 1  # multi-query: one KV head, kept whole on every rank (flash_santacoder_modeling.py:214-224)
+        layout = getattr(type(self.model), "kv_cache_layout", None)
+        if layout is not None:  # multi-query / grouped families say how many KV heads there are and whether they shard
+            kv_heads, kv_world = layout(cfg, world)
         self.kv_cache_manager = PagedKVCacheManager(
             cfg.num_hidden_layers, cfg.num_attention_heads, cfg.hidden_size, kv_heads=kv_heads,
             tensor_parallel_size=kv_world, dtype=dtype, device=self.device, total_num_gpu_blocks=num_kv_blocks, block_size=16)
