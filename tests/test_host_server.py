@@ -123,3 +123,29 @@ def test_servicer_batch_cache_semantics():
         run(svc._next_token(pb.NextTokenRequest(batches=[])))
     with pytest.raises(ValueError):
         run(svc._prefill(pb.PrefillRequest(batch=_pb_batch(3, [1]), to_prune=[_cached(55, [1])])))
+
+
+def test_get_model_rejects_what_is_out_of_scope(tmp_path):
+    """models/__init__.py: get_model - only local directories of flash decoder families; no CPU form of the model itself"""
+    import json
+    import torch
+    import tgis_b200  # noqa: F401
+    from tgis_b200.models import get_model
+    with pytest.raises(ValueError):
+        get_model("no/such/dir", None, "tgis_native", "float16", None, 2048)
+    t5 = tmp_path / "t5"
+    t5.mkdir()
+    (t5 / "config.json").write_text(json.dumps({"model_type": "t5"}))
+    with pytest.raises(NotImplementedError):
+        get_model(str(t5), None, "hf_transformers", "float16", None, 2048)
+    llama = tmp_path / "llama"
+    llama.mkdir()
+    (llama / "config.json").write_text(json.dumps({"model_type": "llama", "hidden_size": 64, "num_attention_heads": 4,
+                                                   "num_hidden_layers": 1, "intermediate_size": 128, "vocab_size": 100}))
+    with pytest.raises(ValueError):
+        get_model(str(llama), None, "tgis_native", "float16", "bitsandbytes", 2048)
+    with pytest.raises(ValueError):
+        get_model(str(llama), None, "tgis_native", "float17", None, 2048)
+    if not torch.cuda.is_available():
+        with pytest.raises(NotImplementedError):  # "FlashCausalLM is only available on GPU": no CPU fallback
+            get_model(str(llama), None, "tgis_native", "float16", None, 2048)
