@@ -47,6 +47,8 @@ class InferenceEngine:
         self.device = torch.device("cuda", device_index)
 
         model_type = self._config.model_type
+        if model_type == "gpt2" and "--bigcode--" in model_path:  # tgis_native.py:37-38: starcoder checkpoints
+            model_type = "gpt_bigcode"
         if model_type not in FLASH_TYPES:
             raise NotImplementedError(f"Flash attention currently only supported by the following model types: {FLASH_TYPES}")
         aliases = None
