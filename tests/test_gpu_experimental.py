@@ -18,16 +18,17 @@ SWITCHES = [
     ("B200_W4_CLUSTER", "tests/test_gpu_gemm.py"),                                # int4 GEMM: stream-K fix-up over DSMEM
     ("B200_F16_ALIGNED", "tests/test_gpu_gemm.py"),                               # fp16 GEMM: aligned stream-K cuts
     ("B200_P2P_ALLREDUCE", "tests/test_gpu_tp.py"),                               # TP boundary over NVLink peer memory (2 GPUs)
-    # GPT-NeoX greedy decode through the fused-step protocol + CUDA graph (single GPU, and TP = 2 when there are 2 GPUs)
-    ("B200_NEOX_FUSED", "tests/test_gpu_neox.py::test_neox_generate_token_through_the_batch_api "
-                        "tests/test_gpu_tp.py::test_tp2_neox_generate_matches_oracle"),
+    # GPT-NeoX / Santacoder greedy decode through the fused-step protocol + CUDA graph (single GPU, and TP = 2 when there are 2 GPUs)
+    ("B200_PY_FUSED_STEP", "tests/test_gpu_neox.py::test_neox_generate_token_through_the_batch_api "
+                           "tests/test_gpu_tp.py::test_tp2_neox_generate_matches_oracle "
+                           "tests/test_gpu_santacoder.py::test_santacoder_generate_token_through_the_batch_api"),
 ]
 
 
 @pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1", reason="experimental kernel variants: set B200_EXPERIMENTAL=1")
 @pytest.mark.parametrize("switch,target", SWITCHES, ids=[s for s, _ in SWITCHES])
 def test_switch_keeps_parity(switch, target):
-    env = dict(os.environ, B200_EXPERIMENTAL="0")
+    env = dict(os.environ)  # B200_EXPERIMENTAL stays set: some targets are opt-in themselves (none of them is this file)
     env[switch] = "1"
     run = subprocess.run([sys.executable, "-m", "pytest", *target.split(), "-x", "-q", "-m", "gpu"], cwd=ROOT, env=env,
                          capture_output=True, text=True, timeout=1200)

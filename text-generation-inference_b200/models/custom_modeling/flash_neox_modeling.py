@@ -12,8 +12,6 @@ Python (no C++ step runtime / CUDA graph yet); the two residual adds of the para
 """
 from __future__ import annotations
 
-import os
-from dataclasses import dataclass
 from typing import Optional
 
 import torch
@@ -25,6 +23,7 @@ from ...utils.flash_attn import PagedKVLayer, attention
 from ...utils.layers import (FastLayerNorm, PositionRotaryEmbedding, TensorParallelColumnLinear, TensorParallelEmbedding,
                              TensorParallelHead, TensorParallelRowLinear, get_linear)
 from ...utils.paged import PagedKVCacheManager, PagedKVState
+from .python_step import PythonFusedGreedy
 
 
 def load_row(config, prefix: str, weights, bias: bool):
@@ -160,27 +159,7 @@ class FlashGPTNeoXModel(nn.Module):
         return hidden_states, past_key_values
 
 
-@dataclass
-class NeoxStep:
-    """What `make_step` hands to FlashCausalLM for this family: the caller's index tensors and output buffers."""
-    T: int
-    B: int
-    max_s: int
-    input_ids: torch.Tensor
-    position_ids: torch.Tensor
-    kv: PagedKVState
-    logits: torch.Tensor
-    next_ids: Optional[torch.Tensor]
-    banned: Optional[torch.Tensor]  # per-row banned id of the arg-max (min_new_tokens EOS mask), set by the caller
-    decode_marker: torch.Tensor
-    banned_ids: int = 0             # the C struct's field of the same name (FlashCausalLM sets both)
-
-
-class _NoScratch:
-    version = 0  # FlashCausalLM keys its cached step on this; nothing here is ever re-allocated
-
-
-class FlashGPTNeoXForCausalLM(nn.Module):
+class FlashGPTNeoXForCausalLM(PythonFusedGreedy, nn.Module):
     def __init__(self, config, weights):
         super().__init__()
         self.config = config
@@ -189,7 +168,6 @@ class FlashGPTNeoXForCausalLM(nn.Module):
         self.gpt_neox = FlashGPTNeoXModel(config, weights)
         self.embed_out = TensorParallelHead.load(config, prefix="embed_out", weights=weights)
         self.max_positions = int(getattr(config, "max_position_embeddings", 2048) or 2048)
-        self.scratch = _NoScratch()
 
     # the attributes FlashCausalLM / the server read on a flash model
     @property
@@ -211,26 +189,7 @@ class FlashGPTNeoXForCausalLM(nn.Module):
     def get_input_embeddings(self) -> nn.Module:
         return self.gpt_neox.embed_in
 
-    # ---------------------------------------------------------------- fused greedy decode (FlashCausalLM._decode_fused_greedy)
-    # EXPERIMENTAL, B200_NEOX_FUSED=1: the same op-by-op decode forward, enqueued into the caller's logits / next-id buffers
-    # and finished by the in-step arg-max, so FlashCausalLM can chain the ids on the device and replay the step as a CUDA
-    # graph (the torch temporaries of the forward then come from the graph's private pool).  Not validated on a GPU yet.
-    fused_greedy_enabled = os.environ.get("B200_NEOX_FUSED", "0") == "1"
-
-    def make_step(self, *, T: int, B: int, is_prefill: bool, max_s: int, input_ids, position_ids, kv: PagedKVState,
-                  cu_seqlens=None, head_rows=None, logits=None, next_ids=None, inputs_embeds=None) -> "NeoxStep":
-        if is_prefill or head_rows is not None or inputs_embeds is not None:
-            raise NotImplementedError("the NeoX fused step is decode-only")
-        # any non-None cu_seqlens_q selects the decode branch of FlashNeoxAttention.forward; the kernels never read it
-        marker = torch.zeros(1, dtype=torch.int32, device=input_ids.device)
-        return NeoxStep(T=T, B=B, max_s=int(max_s), input_ids=input_ids, position_ids=position_ids, kv=kv, logits=logits,
-                        next_ids=next_ids, banned=None, decode_marker=marker)
-
-    def run_step(self, s: "NeoxStep") -> None:
-        hidden, _ = self.gpt_neox(s.input_ids, s.position_ids, None, s.decode_marker, s.max_s, None, s.kv)
-        s.logits.copy_(self.embed_out.linear(hidden))  # this rank's vocab rows; FlashCausalLM gathers them when sharded
-        if s.next_ids is not None:
-            _ops().argmax(s.logits, s.banned, out=s.next_ids)
+    # fused greedy decode (make_step / run_step): python_step.PythonFusedGreedy, off by default
 
     def forward(self, input_ids, position_ids, cu_seqlens, cu_seqlens_q, max_s, inputs_embeds: Optional[torch.Tensor] = None,
                 past_key_values: Optional[PagedKVState] = None, pre_allocate_past_size: Optional[int] = None,

@@ -28,6 +28,7 @@ from ...utils.flash_attn import PagedKVLayer, attention
 from ...utils.layers import (FastLayerNorm, PositionRotaryEmbedding, TensorParallelColumnLinear, TensorParallelEmbedding,
                              TensorParallelHead, TensorParallelRowLinear, get_linear)
 from ...utils.paged import PagedKVCacheManager, PagedKVState
+from .python_step import PythonFusedGreedy
 
 MAX_GROUP = 16  # query heads per KV head in one decode-attention launch (csrc/attn_decode.cu)
 RW_MODEL_TYPES = ("falcon", "RefinedWeb", "RefinedWebModel")
@@ -272,7 +273,7 @@ class FlashRWModel(nn.Module):
         return hidden_states, past_key_values
 
 
-class FlashRWForCausalLM(nn.Module):
+class FlashRWForCausalLM(PythonFusedGreedy, nn.Module):
     def __init__(self, config, weights):
         super().__init__()
         config = RWConfig.of(config)

@@ -27,6 +27,7 @@ from ...utils.flash_attn import PagedKVLayer, attention
 from ...utils.layers import (FastLayerNorm, TensorParallelColumnLinear, TensorParallelEmbedding, TensorParallelHead,
                              TensorParallelRowLinear, get_linear)
 from ...utils.paged import PagedKVCacheManager, PagedKVState
+from .python_step import PythonFusedGreedy
 
 MAX_GROUP = 16  # query heads per KV head in one decode-attention launch (csrc/attn_decode.cu)
 
@@ -209,7 +210,7 @@ class FlashSantacoderModel(nn.Module):
         return hidden_states, past_key_values
 
 
-class FlashSantacoderForCausalLM(nn.Module):
+class FlashSantacoderForCausalLM(PythonFusedGreedy, nn.Module):
     def __init__(self, config, weights):
         super().__init__()
         self.config = config
