@@ -169,3 +169,110 @@ def test_python_fused_step_protocol(tmp_path, monkeypatch):
     assert int(next_ids[1]) == int(second.argmax())
     with pytest.raises(NotImplementedError):
         model.make_step(T=2, B=2, is_prefill=True, max_s=12, input_ids=input_ids, position_ids=position_ids, kv=kv, logits=logits)
+
+
+# ------------------------------------------------------------------------------------------ tensor parallel, world size 2 (gloo)
+def _tp_worker(rank, world, port, family, path, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import tgis_b200  # noqa: F401
+    from tests.dryrun_ops import DryRunOps
+    from tgis_b200.utils import flash_attn, layers
+    from tgis_b200.utils.dist import initialize_torch_distributed
+    from tgis_b200.utils.paged import PagedKVCacheManager, PagedKVState
+    from tgis_b200.utils.weights import Weights
+    fake = DryRunOps()
+    if family == "santacoder":
+        from tgis_b200.models.custom_modeling import flash_santacoder_modeling as m
+        ns = types.SimpleNamespace(model_type="gpt_bigcode", hidden_size=256, n_inner=1024, num_hidden_layers=2, num_attention_heads=4,
+                                   vocab_size=512, n_positions=256, layer_norm_epsilon=1e-5, activation_function="gelu_pytorch_tanh",
+                                   multi_query=True, transpose=False, quantize=None)
+        build, heads, kv_total = m.FlashSantacoderForCausalLM, 4, 1
+    elif family == "falcon_large":
+        from tgis_b200.models.custom_modeling import flash_rw_modeling as m
+        ns = types.SimpleNamespace(model_type="RefinedWeb", hidden_size=512, n_layer=2, n_head=8, n_head_kv=2, vocab_size=384,
+                                   new_decoder_architecture=True, parallel_attn=True, bias=False, layer_norm_epsilon=1e-5,
+                                   multi_query=True, alibi=False, quantize=None, max_position_embeddings=512)
+        build, heads, kv_total = m.FlashRWForCausalLM, 8, 2
+    else:
+        from tgis_b200.models.custom_modeling import flash_neox_modeling as m
+        ns = types.SimpleNamespace(model_type="gpt_neox", hidden_size=256, intermediate_size=1024, num_hidden_layers=2,
+                                   num_attention_heads=4, vocab_size=512, rotary_pct=0.25, rotary_emb_base=10000.0, layer_norm_eps=1e-5,
+                                   use_parallel_residual=(family == "neox_parallel"), hidden_act="gelu", quantize=None,
+                                   max_position_embeddings=512)
+        build, heads, kv_total = m.FlashGPTNeoXForCausalLM, 4, 4
+    for mod in (layers, flash_attn, m):
+        mod._ops = lambda: fake
+    pg = initialize_torch_distributed(world, rank)  # gloo on CPU
+    model = build(ns, Weights([path], device="cpu", dtype=torch.float16, process_group=pg))
+    kv_heads, kv_world = getattr(build, "kv_cache_layout", lambda c, w: (kv_total, w))(ns, world)
+    mgr = model.kv_cache_manager = PagedKVCacheManager(2, heads, ns.hidden_size, kv_heads=kv_heads, tensor_parallel_size=kv_world,
+                                                       device="cpu", total_num_gpu_blocks=16)
+    lens = [7, 18, 2]
+    g = torch.Generator().manual_seed(4)
+    prompts = [torch.randint(0, ns.vocab_size, (L,), generator=g).tolist() for L in lens]
+    sids = mgr.allocate_tokens(lens, reserve_tokens=[3] * 3)
+    kv = PagedKVState(sequence_ids=sids, block_table=mgr.block_table_tensor(sids), context_lens=torch.tensor(lens, dtype=torch.int32),
+                      slot_mapping=mgr.slot_mapping_for(sids, [0] * 3, lens), max_blocks=0)
+    outs = []
+    with torch.inference_mode():
+        cu = torch.tensor([0, 7, 25, 27], dtype=torch.int32)
+        logits, _ = model.forward(torch.tensor([t for p in prompts for t in p]), torch.cat([torch.arange(L) for L in lens]), cu, None,
+                                  max(lens), None, kv, None, (cu[1:] - 1).long())
+        outs.append(logits.clone())
+        nxt = logits.float().argmax(-1)
+        kv.slot_mapping = mgr.slot_mapping_for(sids, lens, [1] * 3)
+        kv.context_lens = torch.tensor([L + 1 for L in lens], dtype=torch.int32)
+        ar = torch.arange(4, dtype=torch.int32)
+        logits, _ = model.forward(nxt, torch.tensor(lens), ar, ar, max(lens) + 1, None, kv, None, None)
+        outs.append(logits.clone())
+    out_q.put((rank, [o.numpy() for o in outs], prompts))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("family", ["santacoder", "falcon_large", "neox_parallel", "neox_sequential"])
+def test_world_size_2_family_wiring_over_gloo(tmp_path, family):
+    """Two CPU ranks over gloo: per-rank head / group / column shards, the replicated multi-query KV head, the all-reduces and
+    the vocab-sharded head gather of the product's host code reproduce the single-rank oracle."""
+    import socket
+    import torch.multiprocessing as mp
+    from safetensors.torch import save_file
+    if family == "santacoder":
+        cfg = osc.SantacoderConfig(256, 1024, 2, 4, 512, n_positions=256)
+        sd, oracle = osc.make_state_dict(cfg, seed=9, std=0.04), None
+        oracle = osc.SantacoderOracle(cfg, sd)
+    elif family == "falcon_large":
+        cfg = ofa.FalconConfig(512, 2, 8, 2, 384, new_decoder_architecture=True, parallel_attn=True)
+        sd = ofa.make_state_dict(cfg, seed=9, std=0.04)
+        oracle = ofa.FalconOracle(cfg, sd)
+    else:
+        cfg = onx.NeoXConfig(256, 1024, 2, 4, 512, rotary_pct=0.25, use_parallel_residual=(family == "neox_parallel"))
+        sd = onx.make_state_dict(cfg, seed=9, std=0.04)
+        oracle = onx.NeoXOracle(cfg, sd)
+    path = os.path.join(str(tmp_path), "model.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tp_worker, args=(r, 2, port, family, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        rank, outs, prompts = q.get(timeout=90)
+        res[rank] = [torch.from_numpy(o) for o in outs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref_tokens, ref_logits = oracle.generate_greedy(prompts, 2)
+    for step in range(2):
+        ref = ref_logits[step].float()
+        # fp16 partial sums of two ranks vs one fp32 accumulation: a few ulp of the activation scale, not 2 ulp of the logits
+        tol = 4e-3 * ref.abs().max().item() + 2e-3
+        for rank in range(2):
+            assert res[rank][step].shape == ref.shape, f"rank {rank}: the vocab shards were not gathered"
+            assert (res[rank][step].float() - ref).abs().max().item() <= tol, f"{family} rank {rank} step {step}"
+        assert torch.equal(res[0][step], res[1][step]), "ranks disagree"

@@ -85,9 +85,10 @@ class TensorParallelHead(SuperLayer):
             return output
         # utils/layers.py:249-277: gather the vocab shards; rank r owns columns [r*V/tp, (r+1)*V/tp)
         world = self.process_group.size()
-        gathered = output.new_empty(world, *output.shape)
+        rows = output.shape[0]
+        gathered = output.new_empty(world * rows, output.shape[1])  # rank-major rows: the shape both NCCL and Gloo accept
         torch.distributed.all_gather_into_tensor(gathered, output.contiguous(), group=self.process_group)
-        return gathered.permute(1, 0, 2).reshape(output.shape[0], -1)
+        return gathered.view(world, rows, -1).permute(1, 0, 2).reshape(rows, -1)
 
 
 class TensorParallelColumnLinear(SuperLayer):
