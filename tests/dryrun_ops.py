@@ -110,8 +110,10 @@ class DryRunOps:
 def patch_ops(monkeypatch, *modules):
     """Points the `_ops` accessor of the given modules (and of the shared layers / attention wrappers) at a DryRunOps."""
     import tgis_b200  # noqa: F401
+    from tgis_b200.models.custom_modeling import python_step
     from tgis_b200.utils import flash_attn, layers
     fake = DryRunOps()
-    for m in (layers, flash_attn, *modules):
-        monkeypatch.setattr(m, "_ops", lambda: fake)
+    for m in (layers, flash_attn, python_step, *modules):
+        if hasattr(m, "_ops"):
+            monkeypatch.setattr(m, "_ops", lambda: fake)
     return fake

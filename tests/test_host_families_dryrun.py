@@ -200,8 +200,10 @@ def _tp_worker(rank, world, port, family, path, out_q):
                                    use_parallel_residual=(family == "neox_parallel"), hidden_act="gelu", quantize=None,
                                    max_position_embeddings=512)
         build, heads, kv_total = m.FlashGPTNeoXForCausalLM, 4, 4
-    for mod in (layers, flash_attn, m):
-        mod._ops = lambda: fake
+    from tgis_b200.models.custom_modeling import python_step
+    for mod in (layers, flash_attn, python_step, m):
+        if hasattr(mod, "_ops"):
+            mod._ops = lambda: fake
     pg = initialize_torch_distributed(world, rank)  # gloo on CPU
     model = build(ns, Weights([path], device="cpu", dtype=torch.float16, process_group=pg))
     kv_heads, kv_world = getattr(build, "kv_cache_layout", lambda c, w: (kv_total, w))(ns, world)

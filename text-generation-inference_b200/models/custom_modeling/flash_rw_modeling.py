@@ -23,14 +23,11 @@ import torch
 import torch.distributed
 from torch import nn
 
-from ...utils import _ops
-from ...utils.flash_attn import PagedKVLayer, attention
 from ...utils.layers import (FastLayerNorm, PositionRotaryEmbedding, TensorParallelColumnLinear, TensorParallelEmbedding,
-                             TensorParallelHead, TensorParallelRowLinear, get_linear)
+                             TensorParallelHead, get_linear)
 from ...utils.paged import PagedKVCacheManager, PagedKVState
-from .python_step import PythonFusedGreedy
+from .python_step import FlashFamilyForCausalLM, gelu_mlp, paged_attention, row_parallel_linear, run_layers
 
-MAX_GROUP = 16  # query heads per KV head in one decode-attention launch (csrc/attn_decode.cu)
 RW_MODEL_TYPES = ("falcon", "RefinedWeb", "RefinedWebModel")
 
 
@@ -85,13 +82,8 @@ class RWConfig:
 
 
 def load_row(config, prefix: str, weights, bias: bool):
-    """:20-33: bias on rank 0 only; with parallel_attn the layer all-reduces attention + MLP once, so the bare linear is returned"""
-    weight = weights.get_multi_weights_row(prefix, quantize=config.quantize)
-    b = weights.get_tensor(f"{prefix}.bias") if bias and weights.process_group.rank() == 0 else None
-    linear = get_linear(weight, b, config.quantize)
-    if config.parallel_attn:
-        return linear
-    return TensorParallelRowLinear(linear, process_group=weights.process_group)
+    """:20-33; with parallel_attn the layer all-reduces attention + MLP once itself"""
+    return row_parallel_linear(config, prefix, weights, bias, reduces_itself=not config.parallel_attn)
 
 
 def load_grouped_qkv(config, prefix: str, weights, groups: int, heads_per_group: int, head_size: int, hidden_size: int):
@@ -109,73 +101,47 @@ def load_grouped_qkv(config, prefix: str, weights, groups: int, heads_per_group:
     return TensorParallelColumnLinear(get_linear(regroup(weight, hidden_size), b, config.quantize))
 
 
-def _paged_attention(module, qkv, n_heads, n_kv, cos_table, sin_table, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q):
-    """Shared by both attention forms once the projection is [q heads | k heads | v heads]: in-place rotary on q and k + KV
-    append (one kernel), then varlen prefill attention or paged decode attention."""
-    d = module.head_size
-    _ops().rope_kv_write_paged(qkv, cos_table, sin_table, position_ids, kv.slot_mapping, k_pool, v_pool, n_heads, n_kv, d)
-    query = qkv[:, :n_heads * d].unflatten(1, (n_heads, d))
-    if cu_seqlens_q is None:
-        key = qkv[:, n_heads * d:(n_heads + n_kv) * d].unflatten(1, (n_kv, d))
-        value = qkv[:, (n_heads + n_kv) * d:].unflatten(1, (n_kv, d))
-        return attention(query, key, value, cu_seqlens, max_s, module.softmax_scale)
-    layer = PagedKVLayer(k_pool, v_pool, kv.block_table, kv.context_lens, int(max_s))
-    if n_heads // n_kv <= MAX_GROUP:
-        return attention(query, layer, None, cu_seqlens, max_s, module.softmax_scale, cu_seqlens_q, 1, False)
-    if n_kv != 1:
-        raise NotImplementedError(f"{n_heads // n_kv} query heads per KV head with {n_kv} KV heads: more than {MAX_GROUP} per launch "
-                                  "is only served for a single shared KV head")
-    out = torch.empty(qkv.shape[0], n_heads, d, dtype=qkv.dtype, device=qkv.device)
-    for g0 in range(0, n_heads, MAX_GROUP):
-        g1 = min(n_heads, g0 + MAX_GROUP)
-        attention(query[:, g0:g1], layer, None, cu_seqlens, max_s, module.softmax_scale, cu_seqlens_q, 1, False, out=out[:, g0:g1])
-    return out
-
-
 class FlashRWAttention(nn.Module):
     def __init__(self, config, prefix, weights):
         super().__init__()
-        self.num_heads = config.n_head
-        self.num_heads_kv = config.n_head_kv
-        self.hidden_size = config.hidden_size
-        self.head_size = self.hidden_size // self.num_heads
-        self.rotary_emb = PositionRotaryEmbedding.static(dim=self.head_size, base=10000.0, device=weights.device)
-        self.softmax_scale = self.head_size ** (-0.5)
         if weights.process_group.size() != 1:
             raise NotImplementedError("the multi-query Falcon form runs on one rank (its fused [q | k | v] rows do not shard evenly by head)")
+        self.num_heads, self.num_heads_kv, self.hidden_size = config.n_head, config.n_head_kv, config.hidden_size
+        self.head_size = self.hidden_size // self.num_heads
+        self.softmax_scale = self.head_size ** (-0.5)
+        self.rotary_emb = PositionRotaryEmbedding.static(dim=self.head_size, base=10000.0, device=weights.device)
         self.query_key_value = TensorParallelColumnLinear.load(config, prefix=f"{prefix}.query_key_value", weights=weights, bias=config.bias)
         self.dense = load_row(config, prefix=f"{prefix}.dense", weights=weights, bias=config.bias)
 
-    def forward(self, hidden_states, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q):
-        qkv = self.query_key_value(hidden_states)  # [T, (h + 2 kv) d] = [q | k | v] already (:156-163)
-        out = _paged_attention(self, qkv, self.num_heads, self.num_heads_kv, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool,
-                               cu_seqlens_q)
+    def forward(self, hidden_states, cos, sin, position_ids, cu_seqlens, max_s, kv, cu_seqlens_q, k_pool, v_pool):
+        # the projection is [q | k | v] already (:156-163)
+        out = paged_attention(self.query_key_value(hidden_states), self.num_heads, self.num_heads_kv, self.head_size, self.softmax_scale,
+                              cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q)
         return self.dense(out.reshape(-1, self.num_heads * self.head_size))
 
 
 class FlashRWLargeAttention(nn.Module):
     def __init__(self, config, prefix, weights):
         super().__init__()
-        hidden_size, num_heads, num_groups = config.hidden_size, config.n_head, config.n_head_kv
-        self.hidden_size = hidden_size
-        self.head_size = hidden_size // num_heads
-        self.num_heads = num_heads // num_groups  # query heads per KV group
-        self.rotary_emb = PositionRotaryEmbedding.static(self.head_size, base=10000.0, device=weights.device)
-        self.softmax_scale = self.head_size ** (-0.5)
-        world = weights.process_group.size()
-        if world > num_groups:
+        world, groups = weights.process_group.size(), config.n_head_kv
+        if world > groups:
             raise NotImplementedError("Tensor Parallelism is not implemented for world_size > n groups")
-        if num_groups % world != 0:
-            raise NotImplementedError(f"Tensor Parallelism is not implemented for {num_groups} not divisible by {world}")
-        self.num_groups = num_groups // world
+        if groups % world != 0:
+            raise NotImplementedError(f"Tensor Parallelism is not implemented for {groups} not divisible by {world}")
+        self.hidden_size = config.hidden_size
+        self.head_size = self.hidden_size // config.n_head
+        self.num_heads = config.n_head // groups  # query heads per KV group
+        self.num_groups = groups // world          # this rank's KV groups
+        self.softmax_scale = self.head_size ** (-0.5)
+        self.rotary_emb = PositionRotaryEmbedding.static(self.head_size, base=10000.0, device=weights.device)
         self.query_key_value = load_grouped_qkv(config, f"{prefix}.query_key_value", weights, self.num_groups, self.num_heads,
-                                                self.head_size, hidden_size)
+                                                self.head_size, self.hidden_size)
         self.dense = load_row(config, prefix=f"{prefix}.dense", weights=weights, bias=config.bias)
 
-    def forward(self, hidden_states, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q):
-        qkv = self.query_key_value(hidden_states)
+    def forward(self, hidden_states, cos, sin, position_ids, cu_seqlens, max_s, kv, cu_seqlens_q, k_pool, v_pool):
         heads = self.num_groups * self.num_heads
-        out = _paged_attention(self, qkv, heads, self.num_groups, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q)
+        out = paged_attention(self.query_key_value(hidden_states), heads, self.num_groups, self.head_size, self.softmax_scale,
+                              cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q)
         return self.dense(out.reshape(-1, heads * self.head_size))
 
 
@@ -186,56 +152,50 @@ class FlashMLP(nn.Module):
         self.dense_4h_to_h = load_row(config, prefix=f"{prefix}.dense_4h_to_h", weights=weights, bias=config.bias)
 
     def forward(self, hidden_states):
-        hidden_states = self.dense_h_to_4h(hidden_states)
-        hidden_states = _ops().gelu(hidden_states, False)  # torch.nn.functional.gelu: the exact form (:331)
-        return self.dense_4h_to_h(hidden_states)
+        return gelu_mlp(self.dense_h_to_4h, self.dense_4h_to_h, hidden_states, False)  # torch.nn.functional.gelu: exact form (:331)
+
+
+def _reduced(branches, process_group):
+    if process_group.size() > 1:
+        torch.distributed.all_reduce(branches, group=process_group)
+    return branches
 
 
 class FlashRWLayer(nn.Module):
     def __init__(self, layer_id, config, weights):
         super().__init__()
-        self.parallel_attn = config.parallel_attn
         prefix = f"transformer.h.{layer_id}"
+        self.parallel_attn = config.parallel_attn
+        self.process_group = weights.process_group
         self.input_layernorm = FastLayerNorm.load(prefix=f"{prefix}.input_layernorm", weights=weights, eps=config.layer_norm_epsilon)
-        self.self_attention = FlashRWAttention(config, prefix=f"{prefix}.self_attention", weights=weights)
         self.post_attention_layernorm = None if self.parallel_attn else FastLayerNorm.load(
             prefix=f"{prefix}.post_attention_layernorm", weights=weights, eps=config.layer_norm_epsilon)
+        self.self_attention = FlashRWAttention(config, prefix=f"{prefix}.self_attention", weights=weights)
         self.mlp = FlashMLP(config, prefix=f"{prefix}.mlp", weights=weights)
-        self.process_group = weights.process_group
 
-    def forward(self, hidden_states, residual, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q):
-        if self.parallel_attn:  # :394-414
-            ln_hidden_states, residual = self.input_layernorm(hidden_states, residual)
-            attn_output = self.self_attention(ln_hidden_states, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q)
-            intermediate = self.mlp(ln_hidden_states) + attn_output
-            if self.process_group.size() > 1:
-                torch.distributed.all_reduce(intermediate, group=self.process_group)
-            return intermediate, residual
-        hidden_states, residual = self.input_layernorm(hidden_states, residual)  # :415-433
-        hidden_states = self.self_attention(hidden_states, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q)
-        hidden_states, residual = self.post_attention_layernorm(hidden_states, residual)
-        return self.mlp(hidden_states), residual
+    def forward(self, hidden_states, residual, *attention_args):
+        normed, residual = self.input_layernorm(hidden_states, residual)
+        if self.parallel_attn:  # :394-414: one LayerNorm feeds both branches; their fp16 sum is all-reduced once
+            return _reduced(self.mlp(normed) + self.self_attention(normed, *attention_args), self.process_group), residual
+        normed, residual = self.post_attention_layernorm(self.self_attention(normed, *attention_args), residual)  # :415-433
+        return self.mlp(normed), residual
 
 
 class FlashRWLargeLayer(nn.Module):
     def __init__(self, layer_id, config, weights):
         super().__init__()
-        prefix = f"transformer.h.{layer_id}"
-        self.ln_attn = FastLayerNorm.load(prefix=f"{prefix}.ln_attn", weights=weights, eps=config.layer_norm_epsilon)
-        self.ln_mlp = FastLayerNorm.load(prefix=f"{prefix}.ln_mlp", weights=weights, eps=config.layer_norm_epsilon)
-        self.self_attention = FlashRWLargeAttention(config, prefix=f"{prefix}.self_attention", weights=weights)
         assert config.parallel_attn, "This version doesn't support non parallel_attn"
-        self.mlp = FlashMLP(config, prefix=f"{prefix}.mlp", weights=weights)
+        prefix = f"transformer.h.{layer_id}"
         self.process_group = weights.process_group
+        for name in ("ln_attn", "ln_mlp"):
+            setattr(self, name, FastLayerNorm.load(prefix=f"{prefix}.{name}", weights=weights, eps=config.layer_norm_epsilon))
+        self.self_attention = FlashRWLargeAttention(config, prefix=f"{prefix}.self_attention", weights=weights)
+        self.mlp = FlashMLP(config, prefix=f"{prefix}.mlp", weights=weights)
 
-    def forward(self, hidden_states, residual, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q):
-        ln_attn, residual = self.ln_attn(hidden_states, residual)
-        ln_mlp, _ = self.ln_mlp(residual)
-        attn_output = self.self_attention(ln_attn, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q)
-        intermediate = attn_output + self.mlp(ln_mlp)
-        if self.process_group.size() > 1:
-            torch.distributed.all_reduce(intermediate, group=self.process_group)
-        return intermediate, residual
+    def forward(self, hidden_states, residual, *attention_args):
+        for_attention, residual = self.ln_attn(hidden_states, residual)  # the residual add happens here ...
+        for_mlp, _ = self.ln_mlp(residual)                               # ... so the MLP's norm reads the updated stream (:469-470)
+        return _reduced(self.self_attention(for_attention, *attention_args) + self.mlp(for_mlp), self.process_group), residual
 
 
 class FlashRWModel(nn.Module):
@@ -244,7 +204,7 @@ class FlashRWModel(nn.Module):
         self.config = config
         self.word_embeddings = TensorParallelEmbedding(prefix="transformer.word_embeddings", weights=weights)
         layer_class = FlashRWLargeLayer if config.new_decoder_architecture else FlashRWLayer
-        self.h = nn.ModuleList([layer_class(layer_id, config, weights) for layer_id in range(config.num_hidden_layers)])
+        self.h = nn.ModuleList(layer_class(n, config, weights) for n in range(config.num_hidden_layers))
         self.ln_f = FastLayerNorm.load(prefix="transformer.ln_f", weights=weights, eps=config.layer_norm_epsilon)
         attn = self.h[0].self_attention
         self.head_size = attn.head_size
@@ -260,29 +220,21 @@ class FlashRWModel(nn.Module):
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         if past_key_values is None:
             raise ValueError("past_key_values must be the batch's PagedKVState (allocate it with kv_cache_manager)")
-        hidden_states = inputs_embeds if inputs_embeds is not None else self.word_embeddings(input_ids)
+        hidden_states = self.word_embeddings(input_ids) if inputs_embeds is None else inputs_embeds
         # fp16 cos / sin tables cached by position (utils/layers.py:436-464); the kernel gathers rows by position_ids
         cos, sin = self.h[0].self_attention.rotary_emb.tables(max(int(max_s), 1), hidden_states.dtype, hidden_states.device)
-        residual = None
-        mgr = self.kv_cache_manager
-        for i, layer in enumerate(self.h):
-            k_pool, v_pool = mgr.layer_pools(i)
-            hidden_states, residual = layer(hidden_states, residual, cos, sin, position_ids, cu_seqlens, max_s, past_key_values,
-                                            k_pool, v_pool, cu_seqlens_q)
-        hidden_states, _ = self.ln_f(hidden_states, residual)
-        return hidden_states, past_key_values
+        hidden_states, residual = run_layers(self.h, self.kv_cache_manager, hidden_states, cos, sin, position_ids, cu_seqlens, max_s,
+                                             past_key_values, cu_seqlens_q)
+        return self.ln_f(hidden_states, residual)[0], past_key_values
 
 
-class FlashRWForCausalLM(PythonFusedGreedy, nn.Module):
+class FlashRWForCausalLM(FlashFamilyForCausalLM):
     def __init__(self, config, weights):
         super().__init__()
         config = RWConfig.of(config)
-        self.config = config
-        self.process_group = weights.process_group
-        self.device = torch.device(weights.device)
+        self._init_outer(config, weights)
         self.transformer = FlashRWModel(config, weights)
         self.lm_head = TensorParallelHead.load(config, prefix="lm_head", weights=weights)
-        self.max_positions = int(getattr(config, "max_position_embeddings", 2048) or 2048)
 
     @staticmethod
     def kv_cache_layout(config, world: int):
@@ -291,28 +243,9 @@ class FlashRWForCausalLM(PythonFusedGreedy, nn.Module):
         config = RWConfig.of(config)
         return (config.n_head_kv, world) if config.new_decoder_architecture else (config.n_head_kv, 1)
 
-    # the attributes FlashCausalLM / the server read on a flash model
     @property
     def model(self):
         return self.transformer
 
-    @property
-    def kv_cache_manager(self):
-        return self.transformer.kv_cache_manager
-
-    @kv_cache_manager.setter
-    def kv_cache_manager(self, mgr):
-        self.transformer.kv_cache_manager = mgr
-
     def get_input_embeddings(self) -> nn.Module:
         return self.transformer.word_embeddings
-
-    def forward(self, input_ids, position_ids, cu_seqlens, cu_seqlens_q, max_s, inputs_embeds: Optional[torch.Tensor] = None,
-                past_key_values: Optional[PagedKVState] = None, pre_allocate_past_size: Optional[int] = None,
-                lm_head_indices: Optional[torch.Tensor] = None):
-        hidden_states, present = self.transformer(input_ids, position_ids, cu_seqlens, cu_seqlens_q, max_s, inputs_embeds,
-                                                  past_key_values, pre_allocate_past_size)
-        if lm_head_indices is not None:
-            hidden_states = hidden_states[lm_head_indices]
-        logits = self.lm_head(hidden_states)
-        return logits, present

@@ -22,14 +22,10 @@ import torch
 import torch.distributed
 from torch import nn
 
-from ...utils import _ops
-from ...utils.flash_attn import PagedKVLayer, attention
 from ...utils.layers import (FastLayerNorm, TensorParallelColumnLinear, TensorParallelEmbedding, TensorParallelHead,
                              TensorParallelRowLinear, get_linear)
 from ...utils.paged import PagedKVCacheManager, PagedKVState
-from .python_step import PythonFusedGreedy
-
-MAX_GROUP = 16  # query heads per KV head in one decode-attention launch (csrc/attn_decode.cu)
+from .python_step import FlashFamilyForCausalLM, gelu_is_tanh, gelu_mlp, paged_attention, row_parallel_linear, run_layers
 
 
 def _q_block_then_kv(view, dim: int, kv_width: int, world: int, rank: int):
@@ -88,11 +84,10 @@ def load_col(config, prefix: str, weights, bias: bool):
 
 
 def load_row(config, prefix: str, weights, bias: bool):
-    if config.transpose:
-        weight = weights.get_sharded(f"{prefix}.weight", dim=0).T.contiguous()
-    else:
-        weight = weights.get_multi_weights_row(prefix, quantize=config.quantize)
-    # the bias is added once: on the first rank, before the all-reduce (:183-187)
+    """:173-190: always all-reduces its own output; GPT2-style checkpoints keep the weight transposed"""
+    if not config.transpose:
+        return row_parallel_linear(config, prefix, weights, bias, reduces_itself=True)
+    weight = weights.get_sharded(f"{prefix}.weight", dim=0).T.contiguous()
     b = weights.get_tensor(f"{prefix}.bias") if bias and weights.process_group.rank() == 0 else None
     return TensorParallelRowLinear(get_linear(weight, b, config.quantize), process_group=weights.process_group)
 
@@ -100,69 +95,51 @@ def load_row(config, prefix: str, weights, bias: bool):
 class FlashMQAttention(nn.Module):
     def __init__(self, prefix, config, weights):
         super().__init__()
-        num_heads = config.num_attention_heads
+        world = weights.process_group.size()
+        total_heads = config.num_attention_heads
+        if total_heads % world != 0:
+            raise ValueError(f"`num_heads` must be divisible by `num_shards` (got `num_heads`: {total_heads} and `num_shards`: {world}")
         self.hidden_size = config.hidden_size
-        self.head_size = self.hidden_size // num_heads
-        if num_heads % weights.process_group.size() != 0:
-            raise ValueError(f"`num_heads` must be divisible by `num_shards` (got `num_heads`: {num_heads} "
-                             f"and `num_shards`: {weights.process_group.size()}")
-        self.num_heads = num_heads // weights.process_group.size()
+        self.num_heads = total_heads // world
+        self.head_size = self.hidden_size // total_heads
         self.softmax_scale = self.head_size ** (-0.5)
         self.c_attn = load_multi_mqa(config, prefix=prefix, weights=weights, bias=True, head_size=self.head_size,
                                      hidden_size=self.hidden_size, num_heads=self.num_heads)
         self.c_proj = load_row(config, prefix=f"{prefix}.c_proj", weights=weights, bias=True)
 
-    def forward(self, hidden_states, identity_cos, identity_sin, position_ids, cu_seqlens, max_s, kv: PagedKVState, k_pool, v_pool,
-                cu_seqlens_q):
-        h, d = self.num_heads, self.head_size
-        qkv = self.c_attn(hidden_states)  # [T, (h + 2) * d] = [q heads | k | v]
-        # KV append (:236 / :250): the RoPE + KV-write kernel with an identity rotation of the first two elements
-        _ops().rope_kv_write_paged(qkv, identity_cos, identity_sin, position_ids, kv.slot_mapping, k_pool, v_pool, h, 1, d, rotary_dim=2)
-        query = qkv[:, :h * d].unflatten(1, (h, d))
-        if cu_seqlens_q is None:  # prefill (:233-246)
-            key = qkv[:, h * d:(h + 1) * d].unflatten(1, (1, d))
-            value = qkv[:, (h + 1) * d:].unflatten(1, (1, d))
-            attn_output = attention(query, key, value, cu_seqlens, max_s, self.softmax_scale)
-        else:  # decode (:248-265): one query token per sequence over the paged cache incl. the token just written
-            layer = PagedKVLayer(k_pool, v_pool, kv.block_table, kv.context_lens, int(max_s))
-            attn_output = torch.empty(qkv.shape[0], h, d, dtype=qkv.dtype, device=qkv.device)
-            for g0 in range(0, h, MAX_GROUP):
-                g1 = min(h, g0 + MAX_GROUP)
-                attention(query[:, g0:g1], layer, None, cu_seqlens, max_s, self.softmax_scale, cu_seqlens_q, 1, False,
-                          out=attn_output[:, g0:g1])
-        return self.c_proj(attn_output.reshape(-1, h * d))
+    def forward(self, hidden_states, identity_cos, identity_sin, position_ids, cu_seqlens, max_s, kv: PagedKVState, cu_seqlens_q,
+                k_pool, v_pool):
+        # c_attn gives [q heads | k | v] (:214-224).  KV placement (:236 / :250) is the RoPE + KV-write kernel with a 2-wide
+        # identity rotation; the single KV head is shared by every query head, 16 of them per decode launch
+        out = paged_attention(self.c_attn(hidden_states), self.num_heads, 1, self.head_size, self.softmax_scale, identity_cos,
+                              identity_sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q, rotary_dim=2)
+        return self.c_proj(out.reshape(-1, self.num_heads * self.head_size))
 
 
 class MLP(nn.Module):
     def __init__(self, prefix, config, weights):
         super().__init__()
-        act = config.activation_function
-        if "gelu" not in act:
-            raise NotImplementedError(f"activation_function {act!r}: only the GELU variants of flash_santacoder_modeling.py:259-270 are built")
-        self.approximate_tanh = act in ["gelu_fast", "gelu_pytorch_tanh"]
+        self.approximate_tanh = gelu_is_tanh(config.activation_function, "flash_santacoder_modeling.py:259-270")
         self.c_fc = load_col(config, prefix=f"{prefix}.c_fc", weights=weights, bias=True)
         self.c_proj = load_row(config, prefix=f"{prefix}.c_proj", weights=weights, bias=True)
 
     def forward(self, hidden_states):
-        hidden_states = self.c_fc(hidden_states)
-        hidden_states = _ops().gelu(hidden_states, self.approximate_tanh)
-        return self.c_proj(hidden_states)
+        return gelu_mlp(self.c_fc, self.c_proj, hidden_states, self.approximate_tanh)
 
 
 class Block(nn.Module):
     def __init__(self, layer_id, config, weights):
         super().__init__()
         prefix = f"transformer.h.{layer_id}"
-        self.ln_1 = FastLayerNorm.load(prefix=f"{prefix}.ln_1", weights=weights, eps=config.layer_norm_epsilon)
-        self.ln_2 = FastLayerNorm.load(prefix=f"{prefix}.ln_2", weights=weights, eps=config.layer_norm_epsilon)
+        for name in ("ln_1", "ln_2"):
+            setattr(self, name, FastLayerNorm.load(prefix=f"{prefix}.{name}", weights=weights, eps=config.layer_norm_epsilon))
         self.attn = FlashMQAttention(prefix=f"{prefix}.attn", config=config, weights=weights)
         self.mlp = MLP(prefix=f"{prefix}.mlp", config=config, weights=weights)
 
-    def forward(self, hidden_states, residual, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q):
-        hidden_states, residual = self.ln_1(hidden_states, residual)
-        hidden_states = self.attn(hidden_states, cos, sin, position_ids, cu_seqlens, max_s, kv, k_pool, v_pool, cu_seqlens_q)
-        hidden_states, residual = self.ln_2(hidden_states, residual)
-        return self.mlp(hidden_states), residual
+    def forward(self, hidden_states, residual, *attention_args):
+        normed, residual = self.ln_1(hidden_states, residual)
+        normed, residual = self.ln_2(self.attn(normed, *attention_args), residual)
+        return self.mlp(normed), residual
 
 
 class FlashSantacoderModel(nn.Module):
@@ -170,13 +147,12 @@ class FlashSantacoderModel(nn.Module):
         super().__init__()
         self.config = config
         self.process_group = weights.process_group
+        # both tables are vocab- / position-sharded without their own all-reduce: the sum is reduced once (:388-389)
         self.wte = TensorParallelEmbedding(prefix="transformer.wte", weights=weights, reduce=False)
         self.wpe = TensorParallelEmbedding(prefix="transformer.wpe", weights=weights, reduce=False)
-        self.h = nn.ModuleList([Block(layer_id, config, weights) for layer_id in range(config.num_hidden_layers)])
+        self.h = nn.ModuleList(Block(n, config, weights) for n in range(config.num_hidden_layers))
         self.ln_f = FastLayerNorm.load(prefix="transformer.ln_f", weights=weights, eps=config.layer_norm_epsilon)
-        self.head_size = self.h[0].attn.head_size
-        self.num_heads = self.h[0].attn.num_heads
-        self.num_key_value_heads = 1
+        self.head_size, self.num_heads, self.num_key_value_heads = self.h[0].attn.head_size, self.h[0].attn.num_heads, 1
         self.kv_cache_manager: Optional[PagedKVCacheManager] = None
         self._identity = None
 
@@ -192,61 +168,32 @@ class FlashSantacoderModel(nn.Module):
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         if past_key_values is None:
             raise ValueError("past_key_values must be the batch's PagedKVState (allocate it with kv_cache_manager)")
-        if inputs_embeds is not None:
-            hidden_states = inputs_embeds + self.wpe(position_ids)
-        else:
-            hidden_states = self.wte(input_ids) + self.wpe(position_ids)
-        if self.process_group.size() > 1:  # both lookups are rank-partial: one all-reduce for the sum (:388-389)
+        tokens = self.wte(input_ids) if inputs_embeds is None else inputs_embeds
+        hidden_states = tokens + self.wpe(position_ids)
+        if self.process_group.size() > 1:
             torch.distributed.all_reduce(hidden_states, group=self.process_group)
-        n_positions = max(int(max_s), int(getattr(self.config, "n_positions", 0) or getattr(self.config, "max_position_embeddings", 0) or 0), 1)
-        cos, sin = self._identity_rotation(n_positions, hidden_states.dtype, hidden_states.device)
-        residual = None
-        mgr = self.kv_cache_manager
-        for i, layer in enumerate(self.h):
-            k_pool, v_pool = mgr.layer_pools(i)
-            hidden_states, residual = layer(hidden_states, residual, cos, sin, position_ids, cu_seqlens, max_s, past_key_values,
-                                            k_pool, v_pool, cu_seqlens_q)
-        hidden_states, _ = self.ln_f(hidden_states, residual)
-        return hidden_states, past_key_values
+        table_rows = max(int(max_s), int(getattr(self.config, "n_positions", 0) or getattr(self.config, "max_position_embeddings", 0) or 0), 1)
+        cos, sin = self._identity_rotation(table_rows, hidden_states.dtype, hidden_states.device)
+        hidden_states, residual = run_layers(self.h, self.kv_cache_manager, hidden_states, cos, sin, position_ids, cu_seqlens, max_s,
+                                             past_key_values, cu_seqlens_q)
+        return self.ln_f(hidden_states, residual)[0], past_key_values
 
 
-class FlashSantacoderForCausalLM(PythonFusedGreedy, nn.Module):
+class FlashSantacoderForCausalLM(FlashFamilyForCausalLM):
     def __init__(self, config, weights):
         super().__init__()
-        self.config = config
-        self.process_group = weights.process_group
-        self.device = torch.device(weights.device)
+        self._init_outer(config, weights)
         self.transformer = FlashSantacoderModel(config, weights)
         self.lm_head = TensorParallelHead.load(config, prefix="transformer.wte", weights=weights)  # tied to the embedding (:447-449)
-        self.max_positions = int(getattr(config, "n_positions", 0) or getattr(config, "max_position_embeddings", 2048) or 2048)
 
     @staticmethod
     def kv_cache_layout(config, world: int):
         """(KV heads in the whole model, ranks they are split over): one head, kept whole on every rank (:214-224)"""
         return 1, 1
 
-    # the attributes FlashCausalLM / the server read on a flash model
     @property
     def model(self):
         return self.transformer
 
-    @property
-    def kv_cache_manager(self):
-        return self.transformer.kv_cache_manager
-
-    @kv_cache_manager.setter
-    def kv_cache_manager(self, mgr):
-        self.transformer.kv_cache_manager = mgr
-
     def get_input_embeddings(self) -> nn.Module:
         return self.transformer.wte
-
-    def forward(self, input_ids, position_ids, cu_seqlens, cu_seqlens_q, max_s, inputs_embeds: Optional[torch.Tensor] = None,
-                past_key_values: Optional[PagedKVState] = None, pre_allocate_past_size: Optional[int] = None,
-                lm_head_indices: Optional[torch.Tensor] = None):
-        hidden_states, present = self.transformer(input_ids, position_ids, cu_seqlens, cu_seqlens_q, max_s, inputs_embeds,
-                                                  past_key_values, pre_allocate_past_size)
-        if lm_head_indices is not None:
-            hidden_states = hidden_states[lm_head_indices]
-        logits = self.lm_head(hidden_states)
-        return logits, present

@@ -3,49 +3,47 @@
 `TextGenerationService` (server.py) keeps the objects returned by `from_pb` in its cache between calls and only ever touches
 them through this interface; `Model.generate_token` mutates them in place.
 """
-from abc import ABC, abstractmethod
-from dataclasses import dataclass
+import abc
+import dataclasses
 from typing import List, Optional, Tuple
 
 import torch
 
-from .. import pb as generate_pb2
+from ..utils.token_types import _Record
 
 
-@dataclass
-class GenerateError:
+@dataclasses.dataclass
+class GenerateError(_Record):
     """A per-request failure that does not fail the whole batch (generate.proto:150-153)."""
+    PB = "GenerateError"
     request_id: int
     message: str
 
-    def to_pb(self):
-        return generate_pb2.GenerateError(request_id=self.request_id, message=self.message)
 
-
-class Batch(ABC):
+class Batch(abc.ABC):
     """What the server needs from a batch type; `FlashCausalLMBatch` is the one implementation on this path."""
 
-    @abstractmethod
+    @abc.abstractmethod
     def get_id(self) -> int:
         """The router's batch id (cache key, cache.py:15-17)."""
 
-    @abstractmethod
+    @abc.abstractmethod
     def __len__(self):
         """Number of live requests."""
 
     @classmethod
-    @abstractmethod
+    @abc.abstractmethod
     def from_pb(cls, pb, tokenizer, dtype: torch.dtype, device: torch.device, embeddings_lookup: Optional, prefix_cache: Optional,
                 use_position_ids: bool = False) -> Tuple["Batch", List[GenerateError]]:
         """Tokenize a `generate.v1.Batch`; requests that fail validation come back as errors, not exceptions."""
 
     @classmethod
-    @abstractmethod
+    @abc.abstractmethod
     def concatenate(cls, batches: List["Batch"]) -> "Batch":
         """Merge cached batches after an add-on prefill (continuous batching); inputs must not be used afterwards."""
 
     @classmethod
-    @abstractmethod
+    @abc.abstractmethod
     def prune(cls, batch: "Batch", completed_ids: List[int]) -> Optional["Batch"]:
         """Drop finished requests; None when nothing is left, the same object when nothing finished."""
 

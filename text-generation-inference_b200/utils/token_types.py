@@ -1,43 +1,65 @@
-"""Token result records returned by `Model.generate_token`.
-Mirrors /root/reference/server/text_generation_server/utils/token_types.py:8-56."""
-from dataclasses import dataclass
-from functools import total_ordering
+"""Per-token results of `Model.generate_token` and their wire form.
+
+The same three records as /root/reference/server/text_generation_server/utils/token_types.py:8-56 (the server and the
+chooser construct them by field name): `TopToken` (a candidate with its log-probability, ordered best first),
+`TokenInfo` (one generated or input token) and `InputTokens` (the echoed prompt of a request).
+"""
+from __future__ import annotations
+
+import dataclasses
 from typing import List, Optional
 
-from .. import pb as generate_pb2
+from .. import pb
 
 
-@dataclass(eq=True)
-@total_ordering
-class TopToken:
+class _Record:
+    """`to_pb()` for a dataclass whose field names are the message's field names."""
+    PB: str = ""
+
+    def to_pb(self):
+        values = {}
+        for name in self.__dataclass_fields__:
+            v = getattr(self, name)
+            values[name] = [item.to_pb() for item in v] if isinstance(v, list) else v
+        return getattr(pb, self.PB)(**values)
+
+
+@dataclasses.dataclass
+class TopToken(_Record):
+    PB = "TopToken"
     token_id: int
     logprob: float = 0.0
 
+    def _rank_key(self):
+        # higher log-probability first; equal log-probabilities resolve to the LOWER token id, the way torch.argmax
+        # resolves ties in greedy decoding (token_types.py:14-18)
+        return (self.logprob, -self.token_id)
+
+    def __lt__(self, other):
+        return self._rank_key() < other._rank_key()
+
+    def __le__(self, other):
+        return self._rank_key() <= other._rank_key()
+
     def __gt__(self, other):
-        # equal logprobs tie-break on the lower token id, like torch.argmax (token_types.py:14-18)
-        return self.logprob > other.logprob or (self.logprob == other.logprob and self.token_id < other.token_id)
+        return self._rank_key() > other._rank_key()
 
-    def to_pb(self):
-        return generate_pb2.TopToken(token_id=self.token_id, logprob=self.logprob)
+    def __ge__(self, other):
+        return self._rank_key() >= other._rank_key()
 
 
-@dataclass
-class TokenInfo:
+@dataclasses.dataclass
+class TokenInfo(_Record):
+    PB = "Token"
     token_id: int
-    request_id: int = 0
+    request_id: int = 0  # not meaningful for input tokens
     logprob: float = 0.0
     rank: int = 0
     top_tokens: Optional[List[TopToken]] = None
 
-    def to_pb(self):
-        return generate_pb2.Token(request_id=self.request_id, token_id=self.token_id, logprob=self.logprob, rank=self.rank,
-                                  top_tokens=None if self.top_tokens is None else [tt.to_pb() for tt in self.top_tokens])
 
-
-@dataclass
-class InputTokens:
+@dataclasses.dataclass
+class InputTokens(_Record):
+    PB = "InputTokens"
     request_id: int
     tokens: List[TokenInfo]
-
-    def to_pb(self):
-        return generate_pb2.InputTokens(request_id=self.request_id, tokens=[t.to_pb() for t in self.tokens])
