@@ -177,3 +177,38 @@ def test_concatenate_and_prune_are_kv_free_and_exact(tmp_path):
     assert got[1][:n1] == ref[1][:n1]
     assert sum(n_ex.values()) >= 20, "test case too weak"
     assert mgr.free_blocks == mgr.total_num_gpu_blocks, "every block returned after all requests finished"
+
+
+@pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1", reason="new this round, not yet run on a GPU: set B200_EXPERIMENTAL=1")
+def test_prompt_prefix_equals_the_same_tokens_typed_in(tmp_path):
+    """flash_causal_lm.py:97-107, :157-168: a request whose prefix embeddings are the embedding rows of some tokens must
+    generate exactly what the request with those tokens prepended to its input generates (same KV, same positions), and the
+    plain request batched with it must be unaffected by going in as embeddings."""
+    from tgis_b200 import pb
+    model, oracle, tok = _setup(tmp_path, None)
+    n_new = 8
+    prefix_ids, tail, other = _prompts(5, [6], 512)[0], _prompts(6, [9], 512)[0], _prompts(7, [14], 512)[0]
+    ref, n_exact = _oracle_tokens(oracle, [prefix_ids + tail, other], n_new)
+    table = model.model.get_input_embeddings().weight
+
+    class Store:
+        def get(self, prefix_id):
+            assert prefix_id == "tuned"
+            return table[torch.tensor(prefix_ids, device=table.device)].clone()
+
+    reqs = _pb_batch(0, [tail, other], n_new).requests
+    reqs[0].prefix_id = "tuned"
+    with torch.inference_mode():
+        batch, errs = model.batch_type.from_pb(pb.Batch(id=0, requests=list(reqs)), tok, torch.float16, model.device,
+                                               model.word_embeddings, Store(), True)
+        assert not errs and batch.input_ids is None and batch.input_lengths == [len(prefix_ids) + len(tail), len(other)]
+        got = [[] for _ in range(2)]
+        out = model.generate_token(batch, first=True)
+        for _ in range(n_new):
+            for t in out[0]:
+                got[t.request_id].append(t.token_id)
+            if len(got[0]) == n_new:
+                break
+            out = model.generate_token(batch)
+    _assert_prefix_equal(got, ref.tolist(), n_exact, min_total=8)
+    model.kv_cache_manager.free_sequences(batch.sequence_ids)

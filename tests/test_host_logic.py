@@ -55,6 +55,36 @@ def test_from_pb_reports_prefix_requests_as_errors(mods):
     assert b is None and len(errs) == 1 and errs[0].request_id == 4
 
 
+def test_from_pb_prepends_prompt_prefixes_as_embeddings(mods):
+    """flash_causal_lm.py:97-107, :147-168: a request with a prefix_id is lengthened by the prefix, its leading positions hold pad
+    ids in all_input_ids_tensor, and the whole batch goes in as embeddings with the prefix rows filled in; a failed lookup
+    only drops that request."""
+    pb, Batch, tok = mods["pb"], mods["Batch"], mods["tok"]
+    H = 8
+    table = torch.arange(16 * H, dtype=torch.float32).view(16, H)
+    lookup = lambda ids: table[ids].clone()  # noqa: E731
+    prefix = -torch.ones(2, H)
+
+    class Store:
+        def get(self, prefix_id):
+            if prefix_id != "tuned":
+                raise KeyError(prefix_id)
+            return prefix
+
+    plain, tuned, missing = _req(pb, 1, "test test", 2, 3), _req(pb, 2, "test test test", 3, 2), _req(pb, 3, "test", 1, 2)
+    tuned.prefix_id, missing.prefix_id = "tuned", "nope"
+    b, errs = Batch.from_pb(pb.Batch(id=5, requests=[plain, tuned, missing]), tok, torch.float32, torch.device("cpu"), lookup, Store(), True)
+    assert [e.request_id for e in errs] == [3] and len(b) == 2
+    assert b.input_ids is None and b.inputs_embeds.shape == (2 + 5, H)
+    assert b.input_lengths == [2, 5] and b.total_lengths == [5, 7] and b.max_seqlen == 5
+    assert b.cu_seqlens.tolist() == [0, 2, 7] and b.position_ids.tolist() == [0, 1, 0, 1, 2, 3, 4]
+    assert b.all_input_ids_tensor[1].tolist() == [0, 0, 3, 3, 3, 0, 0]            # pad ids where the prefix sits
+    assert torch.equal(b.inputs_embeds[2:4], prefix) and torch.equal(b.inputs_embeds[4:7], table[[3, 3, 3]])
+    assert torch.equal(b.inputs_embeds[0:2], table[[3, 3]])
+    with pytest.raises(ValueError):
+        Batch.from_pb(pb.Batch(id=6, requests=[tuned]), tok, torch.float32, torch.device("cpu"), None, Store(), True)
+
+
 def test_get_indices_to_keep_matches_reference_semantics(mods):
     Model, pb = mods["Model"], mods["pb"]
     reqs = [pb.Request(id=i) for i in (2, 5, 7, 9, 12)]

@@ -65,19 +65,27 @@ class FlashCausalLMBatch(Batch):
         batch_inputs, input_lengths, total_lengths, cu_seqlens = [], [], [], [0]
         max_seqlen = 0
         requests = []
+        prefixes = {}  # index among the accepted requests -> prefix embeddings [P, H] (prompt tuning, :97-107)
         for r in pb.requests:
+            input_length = r.input_length
             if r.prefix_id:
-                # prompt-prefix cache is out of scope here; same error path as a failed lookup (:98-107)
-                message = f"Prefix lookup error for request #{r.id}, prefix id {r.prefix_id}"
-                logging.error(message)
-                errors.append(GenerateError(request_id=r.id, message=message))
-                continue
+                try:
+                    if prefix_cache is None:
+                        raise KeyError(r.prefix_id)  # no prompt store configured (prompt_cache.py is outside this library)
+                    prefix = prefix_cache.get(r.prefix_id)
+                except Exception:
+                    message = f"Prefix lookup error for request #{r.id}, prefix id {r.prefix_id}"
+                    logging.error(message)
+                    errors.append(GenerateError(request_id=r.id, message=message))  # excluded from the batch, reported
+                    continue
+                prefixes[len(requests)] = prefix
+                input_length += prefix.shape[0]  # from here on the request's length includes its prefix
             requests.append(r)
             batch_inputs.append(r.inputs)
-            input_lengths.append(r.input_length)
-            max_seqlen = max(max_seqlen, r.input_length)
-            total_lengths.append(r.input_length + r.max_output_length)
-            cu_seqlens.append(cu_seqlens[-1] + r.input_length)
+            input_lengths.append(input_length)
+            max_seqlen = max(max_seqlen, input_length)
+            total_lengths.append(input_length + r.max_output_length)
+            cu_seqlens.append(cu_seqlens[-1] + input_length)
         if not requests:
             return None, errors
 
@@ -89,20 +97,29 @@ class FlashCausalLMBatch(Batch):
                 toks = toks[-r.input_length:]
                 if getattr(tokenizer, "add_bos_token", False):
                     toks[0] = tokenizer.bos_token_id
-            if len(toks) != input_length:
-                raise ValueError(f"request #{r.id}: input_length {input_length} but {len(toks)} tokens after tokenization")
-            t = torch.tensor(toks, dtype=torch.int64)
-            all_input_ids_tensor[i, :input_length] = t
-            input_ids.append(t)
+            if len(toks) != r.input_length:
+                raise ValueError(f"request #{r.id}: input_length {r.input_length} but {len(toks)} tokens after tokenization")
+            # a prefix occupies the leading positions as pad ids (:147-151); its embeddings replace them below
+            all_input_ids_tensor[i, input_length - r.input_length:input_length] = torch.tensor(toks, dtype=torch.int64)
+            input_ids.append(all_input_ids_tensor[i, :input_length].clone())
             params.append(r.parameters)
             return_logprobs.append(r.details.logprobs)
             position_ids.append(torch.arange(0, input_length))
+        flat_ids = torch.cat(input_ids).to(device, non_blocking=True)
+        inputs_embeds = None
+        if prefixes:  # every request goes in as embeddings as soon as one has a prefix (:157-168)
+            if embeddings_lookup is None:
+                raise ValueError("requests with a prompt prefix need the model's input embedding")
+            inputs_embeds = embeddings_lookup(flat_ids)
+            for i, prefix in prefixes.items():
+                inputs_embeds[cu_seqlens[i]:cu_seqlens[i] + prefix.shape[0], :] = prefix.to(inputs_embeds)
+            flat_ids = None
         chooser = HeterogeneousNextTokenChooser.from_pb(
             pb=params, model_eos_token_id=getattr(tokenizer, "model_eos_token_id", tokenizer.eos_token_id),
             model_pad_token_id=tokenizer.pad_token_id, return_logprobs=return_logprobs, dtype=dtype, device=device)
         return cls(
             batch_id=pb.id, requests=requests,
-            input_ids=torch.cat(input_ids).to(device, non_blocking=True), inputs_embeds=None,
+            input_ids=flat_ids, inputs_embeds=inputs_embeds,
             position_ids=torch.cat(position_ids).to(device, non_blocking=True),
             cu_seqlens=torch.tensor(cu_seqlens, dtype=torch.int32, device=device), cu_seqlens_q=None, max_seqlen=max_seqlen,
             past_key_values=None, input_lengths=input_lengths, total_lengths=total_lengths,
