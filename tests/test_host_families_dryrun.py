@@ -70,7 +70,8 @@ def _weights(tmp_path, sd):
 
 
 NEOX = [("parallel_d64_rot25", onx.NeoXConfig(256, 1024, 2, 4, 512, rotary_pct=0.25, use_parallel_residual=True)),
-        ("sequential_d128_rot100", onx.NeoXConfig(256, 1024, 2, 2, 512, rotary_pct=1.0, use_parallel_residual=False))]
+        ("sequential_d128_rot100", onx.NeoXConfig(256, 1024, 2, 2, 512, rotary_pct=1.0, use_parallel_residual=False)),
+        ("parallel_d128_rot50_tanh", onx.NeoXConfig(512, 2048, 3, 4, 384, rotary_pct=0.5, use_parallel_residual=True, hidden_act="gelu_fast"))]
 
 
 @pytest.mark.parametrize("name,cfg", NEOX, ids=[c[0] for c in NEOX])
