@@ -32,6 +32,12 @@ const char* b200_cuda_peek_error(void); /* debug: pending CUDA runtime error str
 void b200_debug_w4_flags(int flags); /* debug timing experiments (results invalid): 1 no x loads, 2 no MMAs, 4 no weight loads, 8 no dequant math */
 void b200_debug_w4_trace(void* device_buffer); /* debug: [n_ctas][64] u64 phase timestamps of int4 GEMM launches; NULL = off */
 int b200_debug_gemm_plan(int kind, int64_t T, int64_t N, int64_t K, int sms, int32_t* out8); /* tests, host only: stream-K plan of a launch; kind 0 fp16, 1 int4; out = {token tile, k-blocks, feature (super-)tiles, token tiles, units per CTA, CTAs, contributor slots, tiles per unit} */
+/* debug: per-kernel device timeline of a step.  While a buffer of `capacity` uint64 slots is attached, every kernel this
+ * library enqueues is followed by a one-thread kernel storing %globaltimer (ns) into the next slot (slot 0: _begin);
+ * _names writes the newline-separated kernel names in launch order and returns the count.  Serialises the stream. */
+void b200_debug_step_trace(void* device_buffer /* NULL = off */, int capacity);
+void b200_debug_step_trace_begin(void* stream);
+int b200_debug_step_trace_names(char* out /* host */, int64_t capacity);
 /* number of kernels this library has enqueued in this process (bench.py reports the delta as "gpu_launches") */
 int64_t b200_launch_count(void);
 
@@ -159,6 +165,38 @@ int b200_gemm_w4a16(const void* x, const void* packed, const void* bias, void* y
 int b200_gemm_w4a16_ex(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
                        int groupsize, int layout, int act, void* workspace, void* stream);
 
+/* ---- deferred split-K reduction ------------------------------------------------------------------------
+ * At decode sizes every SM streams a K-slice of the weights, so an output tile is the sum of several CTAs' fp32 partials.
+ * Instead of finishing that sum inside the GEMM (a grid-wide wait on the slowest contributor + a second pass, 5-8 us per
+ * launch), the *_deferred GEMMs leave the partials in the workspace and describe them with a B200SplitK; the consumer that
+ * follows in the stream anyway (residual + RMSNorm, RoPE + KV write, SiLU * up, the tensor-parallel all-reduce) adds them up
+ * in contributor order as it reads its input - bit-identical to the in-GEMM fix-up.  A B200SplitK is valid until the next GEMM
+ * that uses the same workspace.  Element (t, n), plain layout: tile = n / 128, unit u = tile / tiles_per_unit,
+ * r = tile % tiles_per_unit, contributors c = 0 .. c_last - c_first with c_first = u nkb / units_per_cta,
+ * c_last = ((u + 1) nkb - 1) / units_per_cta:  partial[(((u max_contrib + c) tiles_per_unit + r) tn + t) 128 + n % 128].
+ * gate|up layout (half_tiles > 0): unit u holds tiles (u, u + half_tiles) as r = 0, 1. */
+typedef struct {
+  const float* partial;
+  const void* bias; /* fp16 [N] or NULL: added to the sum by the consumer */
+  int32_t tiles_per_unit, tn, nkb, units_per_cta, max_contrib, half_tiles, N, T;
+} B200SplitK;
+int b200_gemm_w4a16_deferred(const void* x, const void* packed, const void* bias, int64_t T, int64_t N, int64_t K, int groupsize,
+                             int layout, void* workspace, B200SplitK* splitk /* host, out */, void* stream); /* T <= 128 */
+int b200_gemm_f16_deferred(const void* x, const void* w, const void* bias, int64_t T, int64_t N, int64_t K, void* workspace,
+                           B200SplitK* splitk /* host, out */, void* stream); /* T <= 256 */
+/* consumers.  y[T, N] fp16 = the GEMM's output (plain layout) */
+int b200_splitk_reduce(const B200SplitK* parts, void* y, void* stream);
+/* b200_rmsnorm_residual with h = the deferred GEMM output [T, H] (o_proj / down_proj, H = parts->N) */
+int b200_rmsnorm_residual_splitk(const B200SplitK* h_parts, const void* residual, const void* gamma, void* normed_out,
+                                 void* residual_out, float eps, void* stream);
+/* b200_rope_kv_write_paged with qkv = the deferred fused QKV projection; qkv_out [T, (n_heads + 2 n_kv) d] receives the final
+ * activation (q and k rotated) */
+int b200_rope_kv_write_paged_splitk(const B200SplitK* qkv_parts, void* qkv_out, const void* cos, const void* sin,
+                                    const int64_t* position_ids, const int64_t* slot_mapping, void* k_pool, void* v_pool,
+                                    int n_heads, int n_kv_heads, int head_dim, void* stream);
+/* out [T, N/2] = SiLU(gate) * up of a deferred fused [gate; up] projection (either weight layout), b200_silu_mul's arithmetic */
+int b200_splitk_silu_mul(const B200SplitK* gate_up_parts, void* out, void* stream);
+
 /* ---- paged KV block allocator (host) + per-step bookkeeping (device) -------------------------------------
  * replaces fms-extras PagedKVCacheManager block bookkeeping (models/paged_causal_lm.py:338-353,
  * utils/paged.py:92-134; block size 16).  Block ids index the pools' first dimension. */
@@ -177,7 +215,7 @@ int b200_decode_advance(const int32_t* block_table, int64_t block_table_stride, 
  * One call enqueues a whole prefill / decode step of the Llama graph; replaces the Python op sequence of
  * FlashLlamaForCausalLM.forward (models/custom_modeling/flash_llama_modeling.py:425-540).  All pointers device
  * memory owned by the caller (weights: the model; scratch: the host runtime). */
-/* ---- one-shot all-reduce over NVLink peer memory (EXPERIMENTAL; replaces torch.distributed.all_reduce at the tensor-parallel
+/* ---- one-shot all-reduce over NVLink peer memory (replaces torch.distributed.all_reduce at the tensor-parallel
  * layer boundary, utils/layers.py:303-306, :343-345, for decode-sized messages).  create -> exchange the IPC handles of all
  * ranks (any transport) -> connect -> allreduce (CUDA-graph capturable; every rank must issue the same calls). */
 int b200_p2p_handle_bytes(void);
@@ -186,6 +224,16 @@ int b200_p2p_connect(void* ctx, const void* handles /* [world][b200_p2p_handle_b
 int64_t b200_p2p_max_bytes(void* ctx);
 int b200_p2p_allreduce_f16(void* ctx, void* data /* fp16 [n], in place, sums in rank order with fp32 accumulation */, int64_t n, void* stream);
 void b200_p2p_destroy(void* ctx);
+/* A window serves ONE of the three kernels (allreduce_f16 / allreduce_rmsnorm / argmax): their bookkeeping is per block index.
+ * Fused layer boundary: all-reduce of this rank's partial hidden state (h fp16 [T, H], or h_parts = a deferred row-parallel GEMM)
+ * + residual add + RMSNorm (utils/layers.py:318-322 followed by flash_llama_modeling.py:132-148).  residual NULL (first layer):
+ * residual_out = the reduced hidden state.  T <= 256, T * H * 2 <= max_bytes. */
+int b200_p2p_allreduce_rmsnorm(void* ctx, const void* h, const B200SplitK* h_parts, const void* residual, const void* gamma,
+                               void* normed_out, void* residual_out, int64_t T, int64_t H, float eps, void* stream);
+/* greedy ids of a vocabulary-sharded head without gathering logits (replaces utils/layers.py:249-269 + utils/tokens.py:44-46 for
+ * all-greedy batches): local arg-max, (value, index) pairs over NVLink, ties to the lowest global id.  B <= 256. */
+int b200_p2p_argmax(void* ctx, const void* logits, int64_t* out_ids, int64_t B, int64_t V_local, int64_t ld,
+                    const int64_t* banned_ids /* global ids or -1 */, void* stream);
 
 typedef struct {
   const void* weight;  /* fp16 [N, K], or NULL when GPTQ */
@@ -253,15 +301,21 @@ typedef struct {
   int64_t n_head_rows;
   void* head_in;     /* [n_head_rows, H] scratch when head_rows != NULL */
   void* logits;      /* [rows, vocab_rows_head] fp16 */
-  int64_t* next_ids; /* optional [rows] greedy ids (single-rank only) */
+  int64_t* next_ids; /* optional [rows] greedy ids (sharded head: needs p2p_argmax) */
   const int64_t* banned_ids; /* optional [rows], see b200_argmax */
+  /* decode-sized steps (T <= 128): */
+  int32_t defer_splitk; /* 1: linears leave split-K partials to their consumer kernels (B200SplitK) */
+  int32_t _pad2;
+  void* p2p_norm;   /* tensor parallel: b200_p2p_create window for b200_p2p_allreduce_rmsnorm (the layer boundary runs inside the
+                       step, no host-side collective), or NULL: the caller all-reduces `hidden` between the block calls */
+  void* p2p_argmax; /* tensor parallel: window for b200_p2p_argmax (sharded head -> next_ids), or NULL */
 } B200LlamaStep;
 
 int b200_llama_embed(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream);
 int b200_llama_attn_block(const B200LlamaWeights* w, const B200LlamaStep* s, int layer, void* stream);
 int b200_llama_mlp_block(const B200LlamaWeights* w, const B200LlamaStep* s, int layer, void* stream);
 int b200_llama_head(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream);
-int b200_llama_step(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream); /* tp_size == 1 */
+int b200_llama_step(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream); /* tp_size == 1, or p2p_norm set */
 
 #ifdef __cplusplus
 }

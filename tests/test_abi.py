@@ -29,7 +29,9 @@ def test_header_declares_the_expected_surface():
     syms = _header_symbols()
     for s in ["b200_rmsnorm_residual", "b200_rope_kv_write_paged", "b200_attn_prefill_varlen", "b200_attn_decode_paged",
               "b200_gptq_packed_bytes", "b200_gptq_pack", "b200_gemm_w4a16", "b200_gemm_f16", "b200_silu_mul", "b200_argmax", "b200_embedding",
-              "b200_kv_alloc_create", "b200_kv_alloc_take", "b200_kv_alloc_release", "b200_llama_step"]:
+              "b200_kv_alloc_create", "b200_kv_alloc_take", "b200_kv_alloc_release", "b200_llama_step",
+              "b200_gemm_w4a16_deferred", "b200_gemm_f16_deferred", "b200_rmsnorm_residual_splitk", "b200_rope_kv_write_paged_splitk",
+              "b200_splitk_silu_mul", "b200_splitk_reduce", "b200_p2p_allreduce_rmsnorm", "b200_p2p_argmax"]:
         assert s in syms, s
 
 
@@ -50,7 +52,7 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
     """compile the header with gcc and compare sizeof / offsetof of every struct field with the ctypes mirror"""
     import subprocess
     structs = {"B200Linear": lib.B200Linear, "B200LlamaLayer": lib.B200LlamaLayer, "B200LlamaWeights": lib.B200LlamaWeights,
-               "B200LlamaStep": lib.B200LlamaStep}
+               "B200LlamaStep": lib.B200LlamaStep, "B200SplitK": lib.B200SplitK}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
@@ -84,6 +86,13 @@ def test_host_only_entry_points_work_without_a_gpu(lib):
     assert h.b200_kv_alloc_release(a, rel, 2) == 0 and h.b200_kv_alloc_num_free(a) == 5
     bad = (ctypes.c_int32 * 1)(99)
     assert h.b200_kv_alloc_release(a, bad, 1) == -1
+    # a double free is refused while other blocks are still out, and leaves the free list untouched (block 1 is free, 0 is not)
+    twice = (ctypes.c_int32 * 2)(0, 1)
+    assert h.b200_kv_alloc_release(a, twice, 2) == -1 and b"double free" in h.b200_last_error()
+    assert h.b200_kv_alloc_num_free(a) == 5
+    same = (ctypes.c_int32 * 2)(2, 2)
+    assert h.b200_kv_alloc_release(a, same, 2) == -1 and h.b200_kv_alloc_num_free(a) == 5
+    assert h.b200_kv_alloc_release(a, (ctypes.c_int32 * 3)(0, 2, 4), 3) == 0 and h.b200_kv_alloc_num_free(a) == 8
     h.b200_kv_alloc_destroy(a)
 
 

@@ -1,10 +1,7 @@
 """Flash Falcon / RefinedWeb on the B200 kernels vs the CPU oracle (oracle/falcon.py, itself pinned against the reference's
 own module graph and transformers): prefill + decode logits per step and greedy ids outside the fp16 tie band, for the
 multi-query parallel form (incl. 20 query heads on one KV head: more than one decode launch shares), the sequential form
-with biases, and the grouped large form (two LayerNorms, per-group fused projection re-laid-out at load).
-
-Opt-in (B200_EXPERIMENTAL=1) until it has passed once on a GPU: the family is composed of validated kernels but this host
-code was written after the round's GPU budget was spent."""
+with biases, and the grouped large form (two LayerNorms, per-group fused projection re-laid-out at load)."""
 import os
 import types
 
@@ -13,8 +10,7 @@ import torch
 
 from oracle import falcon as ofa
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1", reason="experimental family: set B200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 

@@ -195,12 +195,11 @@ def test_gemm_w4a16_dequant_bit_exact(ops):
 
 
 # per-rank linears of BASELINE configs not covered above: Llama-3-70B int4 at NUM_SHARD = 8 (hidden 8192, 8 + 2 heads of 128,
-# intermediate 28672 / 8) and Llama-3-8B at bs = 64 / 128.  Opt-in until the sweep has run once on a GPU.
+# intermediate 28672 / 8) and Llama-3-8B at bs = 64 / 128.
 W4_MODEL_SHAPES = [(128, 1280, 8192, 128), (128, 8192, 1024, 128), (128, 7168, 8192, 128), (128, 8192, 3584, 128),
                    (64, 6144, 4096, 128), (64, 28672, 4096, 128), (64, 4096, 14336, 128), (1, 8192, 3584, 128)]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_EXPERIMENTAL") != "1", reason="extra shape sweep: set B200_EXPERIMENTAL=1")
 @pytest.mark.parametrize("T,N,K,gs", W4_MODEL_SHAPES)
 def test_gemm_w4a16_model_shapes(ops, T, N, K, gs):
     test_gemm_w4a16(ops, T, N, K, gs)

@@ -179,7 +179,6 @@ def test_concatenate_and_prune_are_kv_free_and_exact(tmp_path):
     assert mgr.free_blocks == mgr.total_num_gpu_blocks, "every block returned after all requests finished"
 
 
-@pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1", reason="new this round, not yet run on a GPU: set B200_EXPERIMENTAL=1")
 def test_prompt_prefix_equals_the_same_tokens_typed_in(tmp_path):
     """flash_causal_lm.py:97-107, :157-168: a request whose prefix embeddings are the embedding rows of some tokens must
     generate exactly what the request with those tokens prepended to its input generates (same KV, same positions), and the

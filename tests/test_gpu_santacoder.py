@@ -1,10 +1,7 @@
 """Flash Santacoder (gpt_bigcode, multi-query attention) on the B200 kernels vs the CPU oracle (oracle/santacoder.py, itself
 pinned against the reference's own module graph and transformers): prefill + decode logits per step and greedy ids outside
 the fp16 tie band — 4 query heads on the shared KV head, and 24 (more than one decode-attention launch can share: served 16
-at a time), head dims 64 and 128.
-
-Opt-in (B200_EXPERIMENTAL=1) until it has passed once on a GPU: the family is composed of validated kernels but this host
-code was written after the round's GPU budget was spent."""
+at a time), head dims 64 and 128."""
 import os
 import types
 
@@ -13,8 +10,7 @@ import torch
 
 from oracle import santacoder as osc
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1", reason="experimental family: set B200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 

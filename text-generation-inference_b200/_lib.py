@@ -17,6 +17,9 @@ SIGNATURES = {
     "b200_cuda_peek_error": (c_char_p, []),
     "b200_debug_w4_trace": (None, [_P]),
     "b200_debug_w4_flags": (None, [_I]),
+    "b200_debug_step_trace": (None, [_P, _I]),
+    "b200_debug_step_trace_begin": (None, [_P]),
+    "b200_debug_step_trace_names": (_I, [c_char_p, _L]),
     "b200_debug_gemm_plan": (_I, [_I, _L, _L, _L, _I, _P]),
     "b200_rmsnorm_residual": (_I, [_P, _P, _P, _P, _P, _L, _L, _F, _P]),
     "b200_rope_kv_write_paged": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
@@ -54,6 +57,12 @@ SIGNATURES = {
 
 
 
+class B200SplitK(ctypes.Structure):
+    _fields_ = [("partial", _P), ("bias", _P), ("tiles_per_unit", ctypes.c_int32), ("tn", ctypes.c_int32), ("nkb", ctypes.c_int32),
+                ("units_per_cta", ctypes.c_int32), ("max_contrib", ctypes.c_int32), ("half_tiles", ctypes.c_int32),
+                ("N", ctypes.c_int32), ("T", ctypes.c_int32)]
+
+
 class B200Linear(ctypes.Structure):
     _fields_ = [("weight", _P), ("qweight", _P), ("perm", _P), ("_unused", _P), ("bias", _P), ("N", _L), ("K", _L),
                 ("groupsize", ctypes.c_int32), ("layout", ctypes.c_int32)]
@@ -78,11 +87,20 @@ class B200LlamaStep(ctypes.Structure):
                 ("block_table", _P), ("block_table_stride", _L), ("context_lens", _P), ("kv_pool", _P),
                 ("kv_layer_stride_bytes", _L), ("kv_v_offset_bytes", _L), ("hidden", _P), ("residual", _P), ("normed", _P),
                 ("qkv", _P), ("attn_out", _P), ("gate_up", _P), ("act", _P), ("perm_x", _P), ("attn_ws", _P), ("attn_ws_bytes", _L),
-                ("gemm_ws", _P), ("head_rows", _P), ("n_head_rows", _L), ("head_in", _P), ("logits", _P), ("next_ids", _P), ("banned_ids", _P)]
+                ("gemm_ws", _P), ("head_rows", _P), ("n_head_rows", _L), ("head_in", _P), ("logits", _P), ("next_ids", _P), ("banned_ids", _P),
+                ("defer_splitk", ctypes.c_int32), ("_pad2", ctypes.c_int32), ("p2p_norm", _P), ("p2p_argmax", _P)]
 
 
-_WP, _SP = ctypes.POINTER(B200LlamaWeights), ctypes.POINTER(B200LlamaStep)
+_WP, _SP, _KP = ctypes.POINTER(B200LlamaWeights), ctypes.POINTER(B200LlamaStep), ctypes.POINTER(B200SplitK)
 SIGNATURES.update({
+    "b200_gemm_w4a16_deferred": (_I, [_P, _P, _P, _L, _L, _L, _I, _I, _P, _KP, _P]),
+    "b200_gemm_f16_deferred": (_I, [_P, _P, _P, _L, _L, _L, _P, _KP, _P]),
+    "b200_splitk_reduce": (_I, [_KP, _P, _P]),
+    "b200_rmsnorm_residual_splitk": (_I, [_KP, _P, _P, _P, _P, _F, _P]),
+    "b200_rope_kv_write_paged_splitk": (_I, [_KP, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200_splitk_silu_mul": (_I, [_KP, _P, _P]),
+    "b200_p2p_allreduce_rmsnorm": (_I, [_P, _P, _KP, _P, _P, _P, _P, _L, _L, _F, _P]),
+    "b200_p2p_argmax": (_I, [_P, _P, _P, _L, _L, _L, _P, _P]),
     "b200_kv_alloc_create": (_P, [ctypes.c_int32]),
     "b200_kv_alloc_destroy": (None, [_P]),
     "b200_kv_alloc_num_free": (ctypes.c_int32, [_P]),

@@ -228,229 +228,6 @@ attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, c
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Persistent variant (EXPERIMENTAL, off unless B200_ATTN_PERSISTENT=1; not yet validated on a GPU — DESIGN.md §6).
-// 2 CTAs per SM walk the (sequence, kv head, chunk) items with a stride of gridDim.x.  The producer warp's page ring runs
-// across item boundaries, so the per-item pipeline fill, the q load and the 4-warp merge no longer leave HBM idle (the
-// one-item-per-CTA kernel above loses ~1.3 us per item to them, ~12 % of the Llama-3-8B attention time).  The merge
-// scratch is separate from the ring for the same reason.
-template <int D>
-__device__ __forceinline__ void decode_page(uint32_t kb, uint32_t vb, int n_valid, const uint32_t (&qf)[D / 16][4], float (&o)[D / 8][4],
-                                            float& m0, float& m1, float& l0, float& l1, float scale_log2, int lane) {
-  const int tig = lane & 3, mi = lane >> 3, r8 = lane & 7;
-  float sc[2][4];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-    const int row = nt * 8 + r8;
-#pragma unroll
-    for (int kc = 0; kc < D / 32; ++kc) {
-      uint32_t b0, b1, b2, b3;
-      ldmatrix_x4(b0, b1, b2, b3, kb + kv_swizzled_chunk_offset<D>(row, kc * 4 + mi));
-      mma_m16n8k16_f16f32(sc[nt], qf[kc * 2], b0, b1);
-      mma_m16n8k16_f16f32(sc[nt], qf[kc * 2 + 1], b2, b3);
-    }
-  }
-  float mx0 = kNegBig, mx1 = kNegBig;
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const bool ok = nt * 8 + tig * 2 + e < n_valid;
-      sc[nt][e] = ok ? sc[nt][e] * scale_log2 : -INFINITY;
-      sc[nt][2 + e] = ok ? sc[nt][2 + e] * scale_log2 : -INFINITY;
-      mx0 = fmaxf(mx0, sc[nt][e]);
-      mx1 = fmaxf(mx1, sc[nt][2 + e]);
-    }
-  }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-  const float a0 = fast_exp2(m0 - mn0), a1 = fast_exp2(m1 - mn1);
-  m0 = mn0;
-  m1 = mn1;
-  float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      sc[nt][e] = fast_exp2(sc[nt][e] - mn0);
-      sc[nt][2 + e] = fast_exp2(sc[nt][2 + e] - mn1);
-      ps0 += sc[nt][e];
-      ps1 += sc[nt][2 + e];
-    }
-  }
-  l0 = l0 * a0 + ps0;
-  l1 = l1 * a1 + ps1;
-  uint32_t pa[4];
-  pa[0] = pack_half2(sc[0][0], sc[0][1]);
-  pa[1] = pack_half2(sc[0][2], sc[0][3]);
-  pa[2] = pack_half2(sc[1][0], sc[1][1]);
-  pa[3] = pack_half2(sc[1][2], sc[1][3]);
-#pragma unroll
-  for (int dc = 0; dc < D / 16; ++dc) {
-    o[2 * dc][0] *= a0; o[2 * dc][1] *= a0; o[2 * dc][2] *= a1; o[2 * dc][3] *= a1;
-    o[2 * dc + 1][0] *= a0; o[2 * dc + 1][1] *= a0; o[2 * dc + 1][2] *= a1; o[2 * dc + 1][3] *= a1;
-    uint32_t v0, v1, v2, v3;
-    const int row = (mi & 1) * 8 + r8;
-    ldmatrix_x4_trans(v0, v1, v2, v3, vb + kv_swizzled_chunk_offset<D>(row, 2 * dc + (mi >> 1)));
-    mma_m16n8k16_f16f32(o[2 * dc], pa, v0, v1);
-    mma_m16n8k16_f16f32(o[2 * dc + 1], pa, v2, v3);
-  }
-}
-
-// Bytes of shared memory the persistent kernel needs for a GQA group of G heads (ring + barriers + merge scratch).
-template <int D>
-static inline int persistent_smem_bytes(int G) {
-  using S = DecodeSmem<D>;
-  const int ring = (S::kStages * S::kStageBytes + 2 * S::kStages * 8 + 15) & ~15;
-  return ring + kConsumerWarps * G * (S::kMergeStride + 2) * 4;
-}
-
-template <int D>
-__global__ void __launch_bounds__(kDecodeThreads, 2)
-attn_decode_paged_persistent_kernel(const __half* __restrict__ q, int64_t q_token_stride, const __half* __restrict__ k_pool,
-                                    const __half* __restrict__ v_pool, const int32_t* __restrict__ block_table, int64_t bt_stride,
-                                    const int32_t* __restrict__ context_lens, float* __restrict__ part_o,
-                                    float* __restrict__ part_ml, int n_heads, int n_kv, int n_chunks_max, int chunk_tokens,
-                                    float scale_log2, int n_items) {
-  using S = DecodeSmem<D>;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* stages = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
-  uint64_t* empty_bar = full_bar + S::kStages;
-  const int G = n_heads / n_kv;
-  float* mo = reinterpret_cast<float*>(smem + ((S::kStages * S::kStageBytes + 2 * S::kStages * 8 + 15) & ~15));  // [4][G][D+8]
-  float* mml = mo + kConsumerWarps * G * S::kMergeStride;                                                        // [4][G][2]
-
-  pdl_launch_dependents();
-  const int warp = warp_id(), lane = lane_id();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerWarps);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  pdl_wait();
-
-  uint32_t fill = 0;  // page groups this CTA has gone through: ring slot = fill % kStages, on both sides of the ring
-  if (warp == kConsumerWarps) {
-    // ------------------------------------------------------------------ producer warp: one page stream over all items
-    const size_t tile_halves = (size_t)kPageTokens * D;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const int chunk = w % n_chunks_max, hk = (w / n_chunks_max) % n_kv, b = w / (n_chunks_max * n_kv);
-      const int L = context_lens[b];
-      const int tok0 = chunk * chunk_tokens;
-      if (tok0 >= L) continue;
-      const int n_pages = (min(chunk_tokens, L - tok0) + kPageTokens - 1) / kPageTokens;
-      const int n_iters = (n_pages + kPagesPerStage - 1) / kPagesPerStage;
-      const int32_t* bt = block_table + (int64_t)b * bt_stride + tok0 / kPageTokens;
-      const int my_block = lane < n_pages ? bt[lane] : 0;
-      for (int it = 0; it < n_iters; ++it, ++fill) {
-        const int s = fill % S::kStages;
-        const int np = min(kPagesPerStage, n_pages - it * kPagesPerStage);
-        if (lane == 0) {
-          mbar_wait(&empty_bar[s], ((fill / S::kStages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(np * 2 * S::kPageBytes));
-        }
-        for (int p = 0; p < np; ++p) {
-          const int blk = __shfl_sync(0xffffffffu, my_block, it * kPagesPerStage + p);
-          if (lane == 0) {
-            const size_t off = ((size_t)blk * n_kv + hk) * tile_halves;
-            unsigned char* dstK = stages + s * S::kStageBytes + p * S::kPageBytes;
-            unsigned char* dstV = dstK + kPagesPerStage * S::kPageBytes;
-            tma_bulk_g2s(dstK, k_pool + off, S::kPageBytes, &full_bar[s]);
-            tma_bulk_g2s(dstV, v_pool + off, S::kPageBytes, &full_bar[s]);
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------------- consumer warps
-  const int g = lane >> 2, tig = lane & 3;
-  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-    const int chunk = w % n_chunks_max, hk = (w / n_chunks_max) % n_kv, b = w / (n_chunks_max * n_kv);
-    const int L = context_lens[b];
-    const int tok0 = chunk * chunk_tokens;
-    if (tok0 >= L) continue;
-    const int n_tok = min(chunk_tokens, L - tok0);
-    const int n_pages = (n_tok + kPageTokens - 1) / kPageTokens;
-    const int n_iters = (n_pages + kPagesPerStage - 1) / kPagesPerStage;
-
-    uint32_t qf[D / 16][4];
-    {
-      const __half* qb = q + (int64_t)b * q_token_stride + (int64_t)hk * G * D;
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks) {
-        const int col = ks * 16 + tig * 2;
-        qf[ks][0] = g < G ? *reinterpret_cast<const uint32_t*>(qb + g * D + col) : 0u;
-        qf[ks][1] = g + 8 < G ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + col) : 0u;
-        qf[ks][2] = g < G ? *reinterpret_cast<const uint32_t*>(qb + g * D + col + 8) : 0u;
-        qf[ks][3] = g + 8 < G ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + col + 8) : 0u;
-      }
-    }
-    float o[D / 8][4];
-#pragma unroll
-    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float m0 = kNegBig, m1 = kNegBig, l0 = 0.f, l1 = 0.f;
-
-    for (int it = 0; it < n_iters; ++it, ++fill) {
-      const int s = fill % S::kStages;
-      const int page = it * kPagesPerStage + warp;
-      mbar_wait(&full_bar[s], (fill / S::kStages) & 1);
-      if (page < n_pages) {
-        const uint32_t kb = smem_u32(stages + s * S::kStageBytes + warp * S::kPageBytes);
-        decode_page<D>(kb, kb + kPagesPerStage * S::kPageBytes, min(kPageTokens, n_tok - page * kPageTokens), qf, o, m0, m1, l0, l1,
-                       scale_log2, lane);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
-
-    // merge the 4 warps' partials through the scratch (the ring already belongs to the next item)
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    if (g < G) {
-#pragma unroll
-      for (int nt = 0; nt < D / 8; ++nt)
-        *reinterpret_cast<float2*>(&mo[(warp * G + g) * S::kMergeStride + nt * 8 + tig * 2]) = make_float2(o[nt][0], o[nt][1]);
-      if (tig == 0) { mml[(warp * G + g) * 2] = m0; mml[(warp * G + g) * 2 + 1] = l0; }
-    }
-    if (g + 8 < G) {
-#pragma unroll
-      for (int nt = 0; nt < D / 8; ++nt)
-        *reinterpret_cast<float2*>(&mo[(warp * G + g + 8) * S::kMergeStride + nt * 8 + tig * 2]) = make_float2(o[nt][2], o[nt][3]);
-      if (tig == 0) { mml[(warp * G + g + 8) * 2] = m1; mml[(warp * G + g + 8) * 2 + 1] = l1; }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
-    for (int idx = threadIdx.x; idx < G * D; idx += kConsumerWarps * 32) {
-      const int r = idx / D, d = idx % D;
-      float M = kNegBig;
-#pragma unroll
-      for (int cw = 0; cw < kConsumerWarps; ++cw) M = fmaxf(M, mml[(cw * G + r) * 2]);
-      float acc = 0.f, lsum = 0.f;
-#pragma unroll
-      for (int cw = 0; cw < kConsumerWarps; ++cw) {
-        const float f = fast_exp2(mml[(cw * G + r) * 2] - M);
-        acc += f * mo[(cw * G + r) * S::kMergeStride + d];
-        lsum += f * mml[(cw * G + r) * 2 + 1];
-      }
-      const int64_t slot = ((int64_t)b * n_heads + hk * G + r) * n_chunks_max + chunk;
-      part_o[slot * D + d] = acc;
-      if (d == 0) { part_ml[slot * 2] = M; part_ml[slot * 2 + 1] = lsum; }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");  // scratch free for the next item
-  }
-}
-
 template <int D>
 __global__ void attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                                            const int32_t* __restrict__ context_lens, __half* __restrict__ out,
@@ -506,26 +283,9 @@ static int launch_decode(const void* q, int64_t q_token_stride, const void* k_po
   float* part_ml = part_o + (int64_t)B * n_heads * n_chunks * D;
   dim3 grid(n_chunks, n_kv, B);
   b200_timing_mark(B200_TIME_ATTN_DECODE, 0, st);
-  static const bool want_persistent = [] { const char* e = getenv("B200_ATTN_PERSISTENT"); return e && atoi(e) > 0; }();
-  const int persistent_bytes = persistent_smem_bytes<D>(n_heads / n_kv);
-  if (want_persistent && persistent_bytes <= 115712) {  // experimental: two persistent CTAs per SM (see the kernel)
-    static int configured_bytes = 0;
-    if (persistent_bytes > configured_bytes) {
-      cudaError_t e = cudaFuncSetAttribute(attn_decode_paged_persistent_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           persistent_bytes);
-      if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
-      configured_bytes = persistent_bytes;
-    }
-    const int n_items = n_chunks * n_kv * B;
-    const int ctas = n_items < 2 * decode_num_sms() ? n_items : 2 * decode_num_sms();
-    B200_LAUNCH(attn_decode_paged_persistent_kernel<D>, dim3(ctas), dim3(kDecodeThreads), (size_t)persistent_bytes, st,
-                (const __half*)q, q_token_stride, (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens,
-                part_o, part_ml, n_heads, n_kv, n_chunks, chunk_tokens, scale * 1.4426950408889634f, n_items);
-  } else {
-    B200_LAUNCH(attn_decode_paged_kernel<D>, grid, dim3(kDecodeThreads), (size_t)S::kBytes, st, (const __half*)q, q_token_stride,
-                (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o, part_ml, n_heads, n_kv,
+  B200_LAUNCH(attn_decode_paged_kernel<D>, grid, dim3(kDecodeThreads), (size_t)S::kBytes, st, (const __half*)q, q_token_stride,
+              (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o, part_ml, n_heads, n_kv,
                 n_chunks, chunk_tokens, scale * 1.4426950408889634f);
-  }
   b200_timing_mark(B200_TIME_ATTN_DECODE, 1, st);
   b200_count_launches(1);
   B200_LAUNCH(attn_decode_combine_kernel<D>, dim3(n_heads, B), dim3(D), 0, st, (const float*)part_o, (const float*)part_ml, context_lens,

@@ -22,11 +22,16 @@
 void b200_set_last_error(const char* msg);
 
 // launch through b200_launch (PDL attribute) and turn a launch error into a status code
-#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+#define B200_LAUNCH_AS(name, kernel, grid, block, smem, stream, ...)                          \
   do {                                                                                        \
     cudaError_t _e = b200_launch(kernel, grid, block, smem, stream, __VA_ARGS__);             \
     if (_e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(_e)); return B200_ERR_CUDA; } \
+    b200_step_trace_stamp(name, stream);                                                      \
   } while (0)
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...) B200_LAUNCH_AS(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
+// debug (b200_debug_step_trace): a one-thread time-stamp kernel after every launch of the library, so that a step can be
+// decomposed kernel by kernel on the device (serialises the stream: PDL overlap is lost while tracing).  No-op otherwise.
+void b200_step_trace_stamp(const char* kernel_name, cudaStream_t stream);
 void b200_count_launches(int n);  // kernels of this library enqueued so far (bench.py "gpu_launches")
 // event pair around one launch of kernel family `which` when a timing handle is attached (runtime.cu)
 #define B200_TIME_ATTN_DECODE 1

@@ -9,6 +9,9 @@
 //   embedding ................ TensorParallelEmbedding.forward, utils/layers.py:346-357
 //   argmax ................... Greedy, utils/tokens.py:44-46
 #include "common.cuh"
+#include "splitk.cuh"
+
+#include <string>
 
 namespace b200 {
 
@@ -18,12 +21,12 @@ namespace b200 {
 // Optional split-K input: `h` may be `n_parts` fp32 partial matrices [n_parts][T][H] (gemm split-K
 // workspace); they are summed and rounded to fp16 first, which is exactly the GEMM's fp16 output.
 // ------------------------------------------------------------------------------------------------
-template <int kThreads>
+template <int kThreads, bool kSplitK>
 __global__ void __launch_bounds__(kThreads) rmsnorm_residual_kernel(const __half* __restrict__ h,
                                                                       const __half* __restrict__ residual,
                                                                       const __half* __restrict__ gamma,
                                                                       __half* __restrict__ normed, __half* __restrict__ res_out,
-                                                                      int H, float eps) {
+                                                                      int H, float eps, const B200SplitK parts) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -34,14 +37,22 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_residual_kernel(const __half
   const __half* rp = residual ? residual + (size_t)row * H : nullptr;
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < H; i += kThreads * 8) {
-    uint4 hv = *reinterpret_cast<const uint4*>(hp + i);
-    const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
     float x[8];
+    if constexpr (kSplitK) {
+      // h is a deferred GEMM output: sum its fp32 partials and round to fp16 first, which is exactly the GEMM's fp16 result
+      const float4 a = splitk_sum4(parts, row, i), b = splitk_sum4(parts, row, i + 4);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = __half22float2(h2[j]);
-      x[2 * j] = f.x;
-      x[2 * j + 1] = f.y;
+      for (int j = 0; j < 8; ++j) x[j] = __half2float(__float2half_rn(v[j]));
+    } else {
+      uint4 hv = *reinterpret_cast<const uint4*>(hp + i);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(h2[j]);
+        x[2 * j] = f.x;
+        x[2 * j + 1] = f.y;
+      }
     }
     if (rp) {
       uint4 rv = *reinterpret_cast<const uint4*>(rp + i);
@@ -91,17 +102,54 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_residual_kernel(const __half
 }
 
 // ------------------------------------------------------------------------------------------------
+// Deferred split-K consumers without another op to fuse into: materialise the fp16 GEMM output, and the LlamaMLP
+// activation SiLU(gate) * up of a gate|up projection (same arithmetic as silu_mul_kernel on the two fp16 outputs).
+// grid (N / 4 / 256, T); one float4 of columns per thread.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ __half splitk_silu_mul_f16(float gate_acc, float up_acc) {
+  const float g = __half2float(__float2half_rn(gate_acc));
+  const __half a = __float2half_rn(g / (1.f + expf(-g)));
+  return __hmul(a, __float2half_rn(up_acc));
+}
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(__half* __restrict__ y, const B200SplitK parts) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.y;
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (n >= parts.N) return;
+  const float4 a = splitk_sum4(parts, t, n);
+  uint2 o;
+  o.x = pack_half2(a.x, a.y);
+  o.y = pack_half2(a.z, a.w);
+  *reinterpret_cast<uint2*>(y + (size_t)t * parts.N + n) = o;
+}
+__global__ void __launch_bounds__(256) splitk_silu_mul_kernel(__half* __restrict__ out, const B200SplitK parts) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.y;
+  const int I = parts.N / 2;
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (n >= I) return;
+  const float4 g = splitk_sum4(parts, t, n), u = splitk_sum4(parts, t, n + I);
+  __half o[4] = {splitk_silu_mul_f16(g.x, u.x), splitk_silu_mul_f16(g.y, u.y), splitk_silu_mul_f16(g.z, u.z),
+                 splitk_silu_mul_f16(g.w, u.w)};
+  *reinterpret_cast<uint2*>(out + (size_t)t * I + n) = *reinterpret_cast<uint2*>(o);
+}
+
+// ------------------------------------------------------------------------------------------------
 // RoPE (half-split pairs, fp32 math, fp16 tables gathered by position) applied in place to q and k of
 // the fused qkv activation, plus the scatter of k and v into the paged pool.
 // Pool layout per layer: K,V [num_blocks][n_kv][16 tokens][d] fp16, 16-byte chunks XOR-swizzled with
 // (token & 7) so a page-head tile lands bank-conflict-free in shared memory with one bulk copy.
 // grid = (T, n_heads + 2*n_kv); block = d/2 threads... one thread per rotation pair.
 // ------------------------------------------------------------------------------------------------
-template <int kHeadDim>
+// kSplitK: the fused QKV projection arrives as deferred split-K partials (`parts`); the sums, rounded to fp16, are the GEMM
+// output, and qkv receives the final activation.
+template <int kHeadDim, bool kSplitK>
 __global__ void rope_kv_write_kernel(__half* __restrict__ qkv, const __half* __restrict__ cos_t,
                                      const __half* __restrict__ sin_t, const int64_t* __restrict__ position_ids,
                                      const int64_t* __restrict__ slot_mapping, __half* __restrict__ k_pool,
-                                     __half* __restrict__ v_pool, int n_heads, int n_kv, int rot_half) {
+                                     __half* __restrict__ v_pool, int n_heads, int n_kv, int rot_half, const B200SplitK parts) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = blockIdx.x;
@@ -109,7 +157,18 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ qkv, const __half* __r
   const int j = threadIdx.x;    // 0..d/2-1: this thread owns elements j and j + d/2 of the head row
   __half* base = qkv + ((size_t)t * (n_heads + 2 * n_kv) + head) * kHeadDim;
   const bool is_v = head >= n_heads + n_kv;
-  __half lo = base[j], hi = base[j + kHeadDim / 2];
+  __half lo, hi;
+  if constexpr (kSplitK) {
+    lo = __float2half_rn(splitk_sum1(parts, t, head * kHeadDim + j));
+    hi = __float2half_rn(splitk_sum1(parts, t, head * kHeadDim + j + kHeadDim / 2));
+    if (is_v) {  // v is not rotated: it only has to reach qkv (prefill-style readers) and the pool
+      base[j] = lo;
+      base[j + kHeadDim / 2] = hi;
+    }
+  } else {
+    lo = base[j];
+    hi = base[j + kHeadDim / 2];
+  }
   if (!is_v) {
     // rotary_dim = cos.shape[-1] * 2 = 2 rot_half (utils/layers.py:467-469): pairs (x[i], x[i + rot_half]), i < rot_half;
     // elements from 2 rot_half on pass through (GPT-NeoX rotary_pct < 1).  Full rotation (Llama): rot_half == d/2 and
@@ -289,7 +348,10 @@ __global__ void __launch_bounds__(kArgmaxThreads) argmax_kernel(const __half* __
   const int ban = banned ? (int)banned[blockIdx.x] : -1;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  const int V8 = (int)(V & ~7LL);
+  // 16-byte loads need rows that start on a 16-byte boundary; otherwise (e.g. a vocabulary of 32001 after an added pad
+  // token) the whole row takes the scalar loop below
+  const bool vec = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int V8 = vec ? (int)(V & ~7LL) : 0;
   // a thread visits its indices in increasing order, so a strict '>' keeps the first maximum
   for (int i = threadIdx.x * 8; i < V8; i += kArgmaxThreads * 8) {
     const uint4 v = *reinterpret_cast<const uint4*>(row + i);
@@ -402,16 +464,68 @@ extern "C" int b200_rmsnorm_residual(const void* h, const void* residual, const 
   }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)H * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(rmsnorm_residual_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  B200_LAUNCH(rmsnorm_residual_kernel<256>, dim3((unsigned)T), dim3(256), smem, st, (const __half*)h, (const __half*)residual,
-              (const __half*)gamma, (__half*)normed_out, (__half*)residual_out, (int)H, eps);
+  constexpr auto kernel = rmsnorm_residual_kernel<256, false>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_LAUNCH_AS("rmsnorm_residual_kernel", kernel, dim3((unsigned)T), dim3(256), smem, st, (const __half*)h, (const __half*)residual,
+                 (const __half*)gamma, (__half*)normed_out, (__half*)residual_out, (int)H, eps, B200SplitK{});
   b200_count_launches(1);
   return B200_OK;
 }
 
-extern "C" int b200_rope_kv_write_paged_ex(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
-                                           const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads,
-                                           int n_kv_heads, int head_dim, int rotary_dim, void* stream) {
+static bool splitk_ok(const B200SplitK* p, const char* who) {
+  if (!p || !p->partial || p->T <= 0 || p->T > p->tn || p->N <= 0 || p->N % 8 != 0 || p->nkb <= 0 || p->units_per_cta <= 0 ||
+      p->max_contrib <= 0 || p->tiles_per_unit <= 0) {
+    b200_set_last_error((std::string(who) + ": not a valid B200SplitK (it comes from a *_deferred GEMM)").c_str());
+    return false;
+  }
+  return true;
+}
+
+extern "C" int b200_rmsnorm_residual_splitk(const B200SplitK* h_parts, const void* residual, const void* gamma, void* normed_out,
+                                            void* residual_out, float eps, void* stream) {
+  if (!splitk_ok(h_parts, "rmsnorm_residual_splitk")) return B200_ERR_ARG;
+  const int64_t T = h_parts->T, H = h_parts->N;
+  if (H > 16384 || h_parts->half_tiles != 0 || !gamma || !normed_out || !residual || !residual_out) {
+    b200_set_last_error("rmsnorm_residual_splitk: need H <= 16384, the plain layout, non-null residual/gamma/outputs");
+    return B200_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)H * sizeof(float);
+  constexpr auto kernel = rmsnorm_residual_kernel<512, true>;  // more threads: the partial loads are L2-latency bound
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_LAUNCH_AS("rmsnorm_residual_kernel<splitk>", kernel, dim3((unsigned)T), dim3(512), smem, st, (const __half*)nullptr,
+                 (const __half*)residual, (const __half*)gamma, (__half*)normed_out, (__half*)residual_out, (int)H, eps, *h_parts);
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+// y[T, N] fp16 = sum of the partials (+ bias): what the GEMM's own fix-up would have written
+extern "C" int b200_splitk_reduce(const B200SplitK* parts, void* y, void* stream) {
+  if (!splitk_ok(parts, "splitk_reduce") || !y) return B200_ERR_ARG;
+  const int vec = parts->N / 4;
+  B200_LAUNCH(splitk_reduce_kernel, dim3((unsigned)((vec + 255) / 256), (unsigned)parts->T), dim3(256), 0, (cudaStream_t)stream,
+              (__half*)y, *parts);
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+extern "C" int b200_splitk_silu_mul(const B200SplitK* parts, void* out, void* stream) {
+  if (!splitk_ok(parts, "splitk_silu_mul") || !out) return B200_ERR_ARG;
+  if (parts->half_tiles > 0 && parts->N != parts->half_tiles * 256) {
+    b200_set_last_error("splitk_silu_mul: N does not match the gate|up layout");
+    return B200_ERR_ARG;
+  }
+  const int vec = parts->N / 8;  // I / 4 output vectors per row
+  B200_LAUNCH(splitk_silu_mul_kernel, dim3((unsigned)((vec + 255) / 256), (unsigned)parts->T), dim3(256), 0, (cudaStream_t)stream,
+              (__half*)out, *parts);
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+template <bool kSplitK>
+static int rope_kv_write_impl(void* qkv, const void* cos, const void* sin, const int64_t* position_ids, const int64_t* slot_mapping,
+                              void* k_pool, void* v_pool, int64_t T, int n_heads, int n_kv_heads, int head_dim, int rotary_dim,
+                              const B200SplitK& parts, void* stream) {
   if (T == 0) return B200_OK;
   if (rotary_dim <= 0 || rotary_dim > head_dim || rotary_dim % 2 != 0) {
     b200_set_last_error("rope_kv_write_paged: rotary_dim must be even and in (0, head_dim]");
@@ -420,17 +534,38 @@ extern "C" int b200_rope_kv_write_paged_ex(void* qkv, const void* cos, const voi
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)T, n_heads + 2 * n_kv_heads);
   if (head_dim == 128) {
-    B200_LAUNCH(rope_kv_write_kernel<128>, grid, dim3(64), 0, st, (__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids,
-                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, rotary_dim / 2);
+    constexpr auto kernel = rope_kv_write_kernel<128, kSplitK>;
+    B200_LAUNCH_AS(kSplitK ? "rope_kv_write_kernel<splitk>" : "rope_kv_write_kernel", kernel, grid, dim3(64), 0, st, (__half*)qkv,
+                   (const __half*)cos, (const __half*)sin, position_ids, slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads,
+                   n_kv_heads, rotary_dim / 2, parts);
   } else if (head_dim == 64) {
-    B200_LAUNCH(rope_kv_write_kernel<64>, grid, dim3(32), 0, st, (__half*)qkv, (const __half*)cos, (const __half*)sin, position_ids,
-                slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads, n_kv_heads, rotary_dim / 2);
+    constexpr auto kernel = rope_kv_write_kernel<64, kSplitK>;
+    B200_LAUNCH_AS(kSplitK ? "rope_kv_write_kernel<splitk>" : "rope_kv_write_kernel", kernel, grid, dim3(32), 0, st, (__half*)qkv,
+                   (const __half*)cos, (const __half*)sin, position_ids, slot_mapping, (__half*)k_pool, (__half*)v_pool, n_heads,
+                   n_kv_heads, rotary_dim / 2, parts);
   } else {
     b200_set_last_error("rope_kv_write_paged: head_dim must be 64 or 128");
     return B200_ERR_UNSUPPORTED;
   }
   b200_count_launches(1);
   return B200_OK;
+}
+extern "C" int b200_rope_kv_write_paged_ex(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
+                                           const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads,
+                                           int n_kv_heads, int head_dim, int rotary_dim, void* stream) {
+  return rope_kv_write_impl<false>(qkv, cos, sin, position_ids, slot_mapping, k_pool, v_pool, T, n_heads, n_kv_heads, head_dim,
+                                   rotary_dim, B200SplitK{}, stream);
+}
+extern "C" int b200_rope_kv_write_paged_splitk(const B200SplitK* qkv_parts, void* qkv_out, const void* cos, const void* sin,
+                                               const int64_t* position_ids, const int64_t* slot_mapping, void* k_pool, void* v_pool,
+                                               int n_heads, int n_kv_heads, int head_dim, void* stream) {
+  if (!splitk_ok(qkv_parts, "rope_kv_write_paged_splitk") || !qkv_out) return B200_ERR_ARG;
+  if (qkv_parts->half_tiles != 0 || qkv_parts->N != (n_heads + 2 * n_kv_heads) * head_dim) {
+    b200_set_last_error("rope_kv_write_paged_splitk: the partials are not a [T, (n_heads + 2 n_kv) d] projection in the plain layout");
+    return B200_ERR_ARG;
+  }
+  return rope_kv_write_impl<true>(qkv_out, cos, sin, position_ids, slot_mapping, k_pool, v_pool, qkv_parts->T, n_heads, n_kv_heads,
+                                  head_dim, head_dim, *qkv_parts, stream);
 }
 extern "C" int b200_rope_kv_write_paged(void* qkv, const void* cos, const void* sin, const int64_t* position_ids,
                                         const int64_t* slot_mapping, void* k_pool, void* v_pool, int64_t T, int n_heads,
@@ -513,7 +648,7 @@ extern "C" int b200_embedding(const void* table, const int64_t* ids, void* out, 
 extern "C" int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, const int64_t* banned_ids,
                            void* stream) {
   if (B == 0) return B200_OK;
-  if (ld % 8 != 0) { b200_set_last_error("argmax: row stride must be a multiple of 8 halves"); return B200_ERR_ARG; }
+  if (ld < V) { b200_set_last_error("argmax: row stride smaller than the row"); return B200_ERR_ARG; }
   B200_LAUNCH(argmax_kernel, dim3((unsigned)B), dim3(kArgmaxThreads), 0, (cudaStream_t)stream, (const __half*)logits, out_ids, V, ld, banned_ids);
   b200_count_launches(1);
   return B200_OK;

@@ -12,6 +12,7 @@
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2..5 = epilogue (TMEM -> registers -> HBM).
 #include "common.cuh"
 #include "tmap.cuh"
+#include "../../include/b200_tgis.h"
 
 #include <cstdlib>
 
@@ -43,6 +44,7 @@ struct F16Params {
   int units_per_cta;  // contiguous (tile, k-block) units per CTA
   int total_units;    // per token tile
   int max_contrib;    // partial slots per tile
+  int defer;          // 1: leave every tile segment as an fp32 partial for the consumer kernel (B200SplitK), no fix-up
 };
 
 template <int TN>
@@ -163,7 +165,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         uint32_t d[16];
         tmem_ld_32x32b_x16(tmem_d + lane_base + c, d);
         tmem_ld_wait();
-        if (n_contrib == 1) {
+        if (n_contrib == 1 && !p.defer) {
           if (n_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -179,7 +181,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
-      if (n_contrib > 1) {
+      if (n_contrib > 1 && !p.defer) {
         // last-arriving contributor sums the slots in contributor order (deterministic); release / acquire through
         // thread 0's gpu-scope fences around the counter, ordered with the other threads by the named barrier
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -276,7 +278,7 @@ static int f16_num_sms() {
   return n;
 }
 
-static F16Plan plan_f16(int64_t T, int64_t N, int64_t K, int sms) {
+static F16Plan plan_f16(int64_t T, int64_t N, int64_t K, int sms, bool defer = false) {
   F16Plan pl;
   pl.TN = T <= 16 ? 16 : T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : 256;
   pl.nkb = (int)((K + kTileK - 1) / kTileK);
@@ -289,14 +291,9 @@ static F16Plan plan_f16(int64_t T, int64_t N, int64_t K, int sms) {
     const int ctas = total < sms ? total : sms;
     pl.units_per_cta = (total + ctas - 1) / ctas;
     if (pl.units_per_cta < 4 && pl.nkb >= 4) pl.units_per_cta = 4;
-    // experiment for the next round (off by default): B200_F16_ALIGNED=1 prefers the largest aligned cut nkb / d (d = 1, 2, 4, 8)
-    // that still fits the SM count - the int4 kernel gained 15-25 % per launch from not letting CTAs straddle tiles
-    static int aligned = -1;
-    if (aligned < 0) {
-      const char* e = getenv("B200_F16_ALIGNED");
-      aligned = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (aligned) {
+    // prefer the largest aligned cut nkb / d (d = 8, 4, 2, 1) that fits the SM count: a CTA that straddles two tiles pays two
+    // fix-ups (measured on B200, round 2: 17.4 -> 14.4 us at 64 x 4096 x 4096, 47.7 -> 33.9 us at T = 256)
+    if (!defer) {
       for (int d = 8; d >= 1; d >>= 1) {
         if (pl.nkb % d == 0 && (int64_t)pl.n_tiles_n * d <= sms && pl.nkb / d >= 4) { pl.units_per_cta = pl.nkb / d; break; }
       }
@@ -335,7 +332,12 @@ extern "C" int b200_debug_gemm_plan(int kind, int64_t T, int64_t N, int64_t K, i
 
 extern "C" int64_t b200_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K) {
   const F16Plan pl = plan_f16(T, N, K, 148);
-  const int64_t f16 = pl.max_contrib > 1 ? (int64_t)pl.n_tiles_t * pl.n_tiles_n * pl.max_contrib * pl.TN * kTileM * 4 : 0;
+  int64_t f16 = pl.max_contrib > 1 ? (int64_t)pl.n_tiles_t * pl.n_tiles_n * pl.max_contrib * pl.TN * kTileM * 4 : 0;
+  if (pl.n_tiles_t == 1) {  // deferred reduction (one token tile) leaves a partial for every tile, even un-split ones
+    const F16Plan pd = plan_f16(T, N, K, 148, true);
+    const int64_t fd = (int64_t)pd.n_tiles_n * pd.max_contrib * pd.TN * kTileM * 4;
+    if (fd > f16) f16 = fd;
+  }
   const int64_t w4 = b200_w4_partial_bytes(T, N, K);
   return kCounterBytes + (f16 > w4 ? f16 : w4);
 }
@@ -352,7 +354,7 @@ extern "C" int64_t b200_gemm_workspace_bytes_max(int64_t N, int64_t K) {
 
 template <int TN>
 static int launch_gemm_f16(const CUtensorMap* mw, const CUtensorMap* mx, void* y, void* workspace, const void* bias, int T, int N,
-                           const F16Plan& pl, cudaStream_t st) {
+                           const F16Plan& pl, int defer, cudaStream_t st) {
   using C = GemmF16Cfg<TN>;
   static bool configured = false;
   if (!configured) {
@@ -372,6 +374,7 @@ static int launch_gemm_f16(const CUtensorMap* mw, const CUtensorMap* mx, void* y
   p.units_per_cta = pl.units_per_cta;
   p.total_units = pl.n_tiles_n * pl.nkb;
   p.max_contrib = pl.max_contrib;
+  p.defer = defer;
   dim3 grid(pl.n_ctas, pl.n_tiles_t, 1);
   b200_timing_mark(B200_TIME_GEMM_F16, 0, st);
   B200_LAUNCH(gemm_f16_kernel<TN>, grid, dim3(kGemmThreads), (size_t)C::kSmemBytes, st, *mw, *mx, p);
@@ -382,12 +385,18 @@ static int launch_gemm_f16(const CUtensorMap* mw, const CUtensorMap* mx, void* y
 
 // workspace: >= b200_gemm_workspace_bytes(T, N, K) bytes whose first 64 KiB (tile counters) were zeroed once by the
 // caller, or NULL (every CTA then takes whole tiles: no stream-K).
-extern "C" int b200_gemm_f16(const void* x, const void* w, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
-                             void* workspace, void* stream) {
+// splitk != NULL: deferred reduction (see b200_gemm_w4a16_deferred): y is not written.
+static int gemm_f16_impl(const void* x, const void* w, const void* bias, void* y, int64_t T, int64_t N, int64_t K, void* workspace,
+                         B200SplitK* splitk, void* stream) {
   if (T == 0 || N == 0) return B200_OK;
   if (K % 8 != 0 || K < 64) { b200_set_last_error("gemm_f16: need K % 8 == 0 and K >= 64"); return B200_ERR_ARG; }
-  F16Plan pl = plan_f16(T, N, K, f16_num_sms());
-  if (pl.max_contrib > 1 && (!workspace || (int64_t)pl.n_tiles_n * pl.n_tiles_t * 4 > kCounterBytes)) {
+  const bool defer = splitk != nullptr;
+  if (defer && (!workspace || T > 256 || N % 8 != 0)) {
+    b200_set_last_error("gemm_f16_deferred: needs a workspace, T <= 256 (one token tile) and N % 8 == 0");
+    return B200_ERR_UNSUPPORTED;
+  }
+  F16Plan pl = plan_f16(T, N, K, f16_num_sms(), defer);
+  if (!defer && pl.max_contrib > 1 && (!workspace || (int64_t)pl.n_tiles_n * pl.n_tiles_t * 4 > kCounterBytes)) {
     pl.units_per_cta = pl.nkb;
     pl.n_ctas = pl.n_tiles_n;
     pl.max_contrib = 1;
@@ -395,12 +404,34 @@ extern "C" int b200_gemm_f16(const void* x, const void* w, const void* bias, voi
   const CUtensorMap* mw = get_tmap_2d(w, N, K, K, kTileM, kTileK, TmapDtype::kF16, TmapSwizzle::k128B);
   const CUtensorMap* mx = get_tmap_2d(x, T, K, K, pl.TN, kTileK, TmapDtype::kF16, TmapSwizzle::k128B);
   if (!mw || !mx) return B200_ERR_CUDA;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (pl.TN) {
-    case 16: return launch_gemm_f16<16>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, st);
-    case 32: return launch_gemm_f16<32>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, st);
-    case 64: return launch_gemm_f16<64>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, st);
-    case 128: return launch_gemm_f16<128>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, st);
-    default: return launch_gemm_f16<256>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, st);
+  if (defer) {
+    splitk->partial = (const float*)((const char*)workspace + kCounterBytes);
+    splitk->bias = bias;
+    splitk->tiles_per_unit = 1;
+    splitk->tn = pl.TN;
+    splitk->nkb = pl.nkb;
+    splitk->units_per_cta = pl.units_per_cta;
+    splitk->max_contrib = pl.max_contrib;
+    splitk->half_tiles = 0;
+    splitk->N = (int32_t)N;
+    splitk->T = (int32_t)T;
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int df = defer ? 1 : 0;
+  switch (pl.TN) {
+    case 16: return launch_gemm_f16<16>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, df, st);
+    case 32: return launch_gemm_f16<32>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, df, st);
+    case 64: return launch_gemm_f16<64>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, df, st);
+    case 128: return launch_gemm_f16<128>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, df, st);
+    default: return launch_gemm_f16<256>(mw, mx, y, workspace, bias, (int)T, (int)N, pl, df, st);
+  }
+}
+extern "C" int b200_gemm_f16(const void* x, const void* w, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
+                             void* workspace, void* stream) {
+  return gemm_f16_impl(x, w, bias, y, T, N, K, workspace, nullptr, stream);
+}
+extern "C" int b200_gemm_f16_deferred(const void* x, const void* w, const void* bias, int64_t T, int64_t N, int64_t K, void* workspace,
+                                      B200SplitK* splitk, void* stream) {
+  if (!splitk) { b200_set_last_error("gemm_f16_deferred: splitk is NULL"); return B200_ERR_ARG; }
+  return gemm_f16_impl(x, w, bias, nullptr, T, N, K, workspace, splitk, stream);
 }

@@ -43,6 +43,7 @@
 // later use test_wait: try_wait may suspend the thread until a time-out while the phase is pending.
 #include "common.cuh"
 #include "tmap.cuh"
+#include "../../include/b200_tgis.h"
 
 #include <cstdlib>
 #include <string>
@@ -133,21 +134,6 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// ---- thread-block cluster helpers (experimental DSMEM fix-up, B200_W4_CLUSTER=1)
-__device__ __forceinline__ uint32_t mapa_shared_cluster(uint32_t local_addr, uint32_t cta_rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-  return r;
-}
-__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t cluster_addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 // non-blocking poll (mbarrier.try_wait may suspend the thread until a time-out when the phase is still pending)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
@@ -217,13 +203,13 @@ struct W4Params {
   int half_tiles;   // 0: super-tile s = feature tiles (2s, 2s+1); > 0 ("gate|up" layout): tiles (s, s + half_tiles)
   int act;          // 1: y[t, 128 s + m] = fp16(silu(fp16 gate)) * fp16 up  (needs the gate|up layout), row stride ldy
   int ldy;          // output row stride in halves
+  int defer;        // 1: every super-tile segment is left as an fp32 partial in the workspace and the NEXT kernel of the stream sums
+                    //    them (B200SplitK consumers: rmsnorm / rope / SiLU*up / all-reduce); no counters, no waiting on peer CTAs
   unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
 };
 
 // kGR = meta rows per unit record (1, 2 or 4 = 128 / groupsize, 1 for groupsize >= 128).
-// kCluster (experimental, off by default): the CTAs that share a super-tile form a thread-block cluster and exchange their
-// fp32 partials through distributed shared memory instead of the global workspace + counters.
-template <int TN, int kGR, bool kCluster>
+template <int TN, int kGR>
 __global__ void __launch_bounds__(kW4Threads, 1)
 gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) {
   using C = GemmW4Cfg<TN>;
@@ -498,7 +484,7 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
         const int n0 = (p.half_tiles ? sup : sup * kW4R) * kW4TileM + m;
         const int n1 = (p.half_tiles ? sup + p.half_tiles : sup * kW4R + 1) * kW4TileM + m;
         const bool ok0 = n0 < p.N, ok1 = n1 < p.N;
-        const bool direct = n_contrib == 1;
+        const bool direct = n_contrib == 1 && !p.defer;
         const float bv0 = (p.bias && ok0 && direct) ? __half2float(p.bias[n0]) : 0.f;
         const float bv1 = (p.bias && ok1 && direct) ? __half2float(p.bias[n1]) : 0.f;
         constexpr int kCh = TN < 32 ? TN : 32;  // columns fetched per tcgen05.wait::ld
@@ -512,21 +498,11 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
           }
           tmem_ld_wait();
           if (!direct) {
-            if constexpr (kCluster) {
-              // stage the partial in this CTA's own shared memory (the weight ring is idle once the last accumulator is full)
-              const uint32_t stage = smem_u32(w_ring);
 #pragma unroll
-              for (int j = 0; j < kCh; ++j) {
-                sts_f32(stage + (uint32_t)(((c + j) * kW4TileM + m) * 4), __uint_as_float(d0[j]));
-                sts_f32(stage + (uint32_t)(((TN + c + j) * kW4TileM + m) * 4), __uint_as_float(d1[j]));
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < kCh; ++j) {
-                if (t0 + c + j < p.T) {
-                  part[(c + j) * kW4TileM + m] = __uint_as_float(d0[j]);
-                  part[(TN + c + j) * kW4TileM + m] = __uint_as_float(d1[j]);
-                }
+            for (int j = 0; j < kCh; ++j) {
+              if (t0 + c + j < p.T) {
+                part[(c + j) * kW4TileM + m] = __uint_as_float(d0[j]);
+                part[(TN + c + j) * kW4TileM + m] = __uint_as_float(d1[j]);
               }
             }
           } else if (p.act) {
@@ -553,14 +529,12 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       W4_TRACE(9 + (seg & 3) * 2, 0);
-      if (n_contrib > 1) {
+      if (n_contrib > 1 && !p.defer) {
         // release: the epilogue barrier orders every thread's partial stores before thread 0's gpu-scope fence + count
-        if constexpr (!kCluster) asm volatile("bar.sync 1, %0;" ::"n"(kW4EpWarps * 32) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kW4EpWarps * 32) : "memory");
         if (threadIdx.x == 0) {
-          if constexpr (!kCluster) {
-            __threadfence();
-            atomicAdd(&p.counters[2 * tix], 1);
-          }
+          __threadfence();
+          atomicAdd(&p.counters[2 * tix], 1);
           s_fix[nfix][0] = tix;
           s_fix[nfix][1] = sup;
           s_fix[nfix][2] = n_contrib;
@@ -581,58 +555,6 @@ gemm_w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const W4Params p) 
   const int nfix = s_nfix;
   if (nfix > 0) pdl_wait();
   W4_TRACE(40, 0);
-  if constexpr (kCluster) {
-    // every CTA of the cluster shares this CTA's (only) super-tile: contributor index == rank in the cluster
-    static_assert(!kCluster || kW4R * TN * kW4TileM * 4 <= C::kWStages * kW4RecMaxBytes, "partial must fit in the weight ring");
-    cluster_sync_all();  // all partials are staged
-    if (nfix > 0) {
-      const int sup = s_fix[0][1], n_contrib = s_fix[0][2], my_contrib = s_fix[0][3];
-      const uint32_t stage = smem_u32(w_ring);
-      const int rows = min(p.T - t0, TN);
-      const int n_vec = p.act ? rows * (kW4TileM / 4) : kW4R * rows * (kW4TileM / 4);
-      const int per = (n_vec + n_contrib - 1) / n_contrib;
-      const int hi = min(n_vec, (my_contrib + 1) * per);
-      for (int idx = my_contrib * per + (int)threadIdx.x; idx < hi; idx += kW4Threads) {
-        const int r = p.act ? 0 : idx / (rows * (kW4TileM / 4));
-        const int rem = idx - r * rows * (kW4TileM / 4);
-        const int tt = rem / (kW4TileM / 4), mm = (rem % (kW4TileM / 4)) * 4;
-        const uint32_t off = (uint32_t)(((r * TN + tt) * kW4TileM + mm) * 4);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), u = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = 0; c < n_contrib; ++c) {  // contributor order: deterministic
-          const float4 v = ld_dsmem_v4(mapa_shared_cluster(stage + off, (uint32_t)c));
-          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-          if (p.act) {
-            const float4 w = ld_dsmem_v4(mapa_shared_cluster(stage + off + (uint32_t)(TN * kW4TileM * 4), (uint32_t)c));
-            u.x += w.x; u.y += w.y; u.z += w.z; u.w += w.w;
-          }
-        }
-        if (p.act) {
-          const int nn = sup * kW4TileM + mm, nu = nn + p.half_tiles * kW4TileM;
-          if (p.bias) {
-            a.x += __half2float(p.bias[nn]); a.y += __half2float(p.bias[nn + 1]); a.z += __half2float(p.bias[nn + 2]); a.w += __half2float(p.bias[nn + 3]);
-            u.x += __half2float(p.bias[nu]); u.y += __half2float(p.bias[nu + 1]); u.z += __half2float(p.bias[nu + 2]); u.w += __half2float(p.bias[nu + 3]);
-          }
-          __half o[4] = {silu_mul_f16(a.x, u.x), silu_mul_f16(a.y, u.y), silu_mul_f16(a.z, u.z), silu_mul_f16(a.w, u.w)};
-          *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.ldy + nn]) = *reinterpret_cast<uint2*>(o);
-        } else {
-          const int nn = (p.half_tiles ? sup + r * p.half_tiles : sup * kW4R + r) * kW4TileM + mm;
-          if (nn < p.N) {
-            if (p.bias) {
-              a.x += __half2float(p.bias[nn]); a.y += __half2float(p.bias[nn + 1]);
-              a.z += __half2float(p.bias[nn + 2]); a.w += __half2float(p.bias[nn + 3]);
-            }
-            uint2 o;
-            o.x = pack_half2(a.x, a.y);
-            o.y = pack_half2(a.z, a.w);
-            *reinterpret_cast<uint2*>(&p.y[(size_t)(t0 + tt) * p.ldy + nn]) = o;
-          }
-        }
-      }
-    }
-    cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
-    W4_TRACE(63, 0);
-    return;
-  }
   for (int f = 0; f < nfix; ++f) {
     const int tix = s_fix[f][0], sup = s_fix[f][1], n_contrib = s_fix[f][2], my_contrib = s_fix[f][3];
     if (threadIdx.x == 0) {
@@ -806,7 +728,7 @@ struct W4Plan {
 // n_super * d is not close to a multiple of the SM count).  Costs in microseconds fitted to tools/sweep_w4_su.py on B200
 // (cold weights): 0.35 per unit in the main loop, ~1 for a direct epilogue, 4.5-6 for one split-K fix-up (partial store,
 // gpu-scope fence, waiting for the slowest contributor, L2-latency-bound slice reduction), ~10 when CTAs straddle.
-static W4Plan plan_w4(int64_t T, int64_t N, int64_t K, int sms) {
+static W4Plan plan_w4(int64_t T, int64_t N, int64_t K, int sms, bool defer = false) {
   W4Plan pl;
   pl.TN = T <= 16 ? 16 : T <= 32 ? 32 : T <= 64 ? 64 : 128;
   pl.nkb = w4_nkb(K);
@@ -819,8 +741,10 @@ static W4Plan plan_w4(int64_t T, int64_t N, int64_t K, int sms) {
     const int ctas = total < sms ? total : sms;
     int best = (total + ctas - 1) / ctas;
     if (best < 2 && pl.nkb >= 2) best = 2;  // one unit per team at least
+    // deferred reduction (the consumer kernel sums the partials): no in-kernel fix-up, a CTA that straddles two super-tiles only
+    // pays a mid-loop accumulator drain (~1 us)
     auto cost = [&](int su, bool aligned, int d) {
-      const float fix = aligned ? (d == 1 ? 1.0f : 4.5f + 0.2f * d) : 10.0f;
+      const float fix = defer ? (aligned ? 0.f : 1.0f) : (aligned ? (d == 1 ? 1.0f : 4.5f + 0.2f * d) : 10.0f);
       return 0.35f * kW4R * su + fix;
     };
     float best_cost = cost(best, pl.nkb % best == 0, pl.nkb / best);
@@ -921,8 +845,9 @@ extern "C" int b200_gptq_pack(const void* qweight, const void* qzeros, const voi
 // bytes of split-K partials the int4 GEMM may write for this shape (the tile counters sit in the first 64 KiB)
 // The plan a launch uses: the stream-K cut needs the workspace (partials + one counter pair per super-tile) and every CTA
 // resident at once (the fix-up spins on its peers); otherwise each CTA takes whole super-tiles.
-static W4Plan launch_plan_w4(int64_t T, int64_t N, int64_t K, int sms, bool has_workspace) {
-  W4Plan pl = plan_w4(T, N, K, sms);
+static W4Plan launch_plan_w4(int64_t T, int64_t N, int64_t K, int sms, bool has_workspace, bool defer = false) {
+  W4Plan pl = plan_w4(T, N, K, sms, defer);
+  if (defer) return pl;  // the caller checked: one token tile, workspace present; no counters, no co-residency requirement
   if (pl.max_contrib > 1 && (!has_workspace || (int64_t)pl.n_super * pl.n_tiles_t * 8 > kW4CounterBytes || pl.n_ctas > sms)) {
     pl.su_per_cta = pl.nkb;
     pl.n_ctas = pl.n_super;
@@ -940,32 +865,23 @@ void b200_w4_plan_debug(int64_t T, int64_t N, int64_t K, int sms, int32_t* out) 
 
 int64_t b200_w4_partial_bytes(int64_t T, int64_t N, int64_t K) {
   const W4Plan pl = plan_w4(T, N, K, num_sms());
-  if (pl.max_contrib <= 1) return 0;
-  return (int64_t)pl.n_tiles_t * pl.n_super * pl.max_contrib * kW4R * pl.TN * kW4TileM * 4;
-}
-
-// experimental: B200_W4_CLUSTER=1 runs aligned 2 / 4 / 8-way shared super-tiles as thread-block clusters (DSMEM fix-up)
-static bool w4_cluster_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200_W4_CLUSTER");
-    v = (e && e[0] == '1') ? 1 : 0;
+  int64_t need = pl.max_contrib <= 1 ? 0 : (int64_t)pl.n_tiles_t * pl.n_super * pl.max_contrib * kW4R * pl.TN * kW4TileM * 4;
+  if (pl.n_tiles_t == 1) {  // deferred reduction: every super-tile has at least one partial slot
+    const W4Plan pd = plan_w4(T, N, K, num_sms(), true);
+    const int64_t nd = (int64_t)pd.n_super * pd.max_contrib * kW4R * pd.TN * kW4TileM * 4;
+    if (nd > need) need = nd;
   }
-  return v == 1;
+  return need;
 }
 
 template <int TN, int kGR>
 static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, void* workspace, const void* bias, int T, int N,
-                          const W4Plan& pl, int half_tiles, int act, cudaStream_t st) {
+                          const W4Plan& pl, int half_tiles, int act, int defer, cudaStream_t st) {
   using C = GemmW4Cfg<TN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN, kGR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN, kGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
-    if constexpr (TN <= 64) {
-      e = cudaFuncSetAttribute(gemm_w4a16_kernel<TN, kGR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-      if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
-    }
     configured = true;
   }
   W4Params p;
@@ -985,34 +901,12 @@ static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, vo
   p.half_tiles = half_tiles;
   p.act = act;
   p.ldy = act ? N / 2 : N;
+  p.defer = defer;
   p.trace = g_w4_trace;
   dim3 grid(pl.n_ctas, pl.n_tiles_t, 1);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 0, st);
-  const int d = pl.su_per_cta > 0 ? pl.nkb / pl.su_per_cta : 0;  // CTAs per super-tile when the cut is aligned
-  bool clustered = false;
-  if constexpr (TN <= 64) {
-    if (w4_cluster_enabled() && pl.n_tiles_t == 1 && pl.max_contrib > 1 && pl.nkb % pl.su_per_cta == 0 && (d == 2 || d == 4 || d == 8) &&
-        pl.n_ctas == pl.n_super * d) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = grid;
-      cfg.blockDim = dim3(kW4Threads);
-      cfg.dynamicSmemBytes = (size_t)C::kSmemBytes;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[2];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = (unsigned)d;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[1].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = b200_pdl_enabled() ? 2 : 1;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_w4a16_kernel<TN, kGR, true>, *mx, p);
-      if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
-      clustered = true;
-    }
-  }
-  if (!clustered) B200_LAUNCH(gemm_w4a16_kernel<TN, kGR, false>, grid, dim3(kW4Threads), (size_t)C::kSmemBytes, st, *mx, p);
+  constexpr auto kernel = gemm_w4a16_kernel<TN, kGR>;
+  B200_LAUNCH_AS("gemm_w4a16_kernel", kernel, grid, dim3(kW4Threads), (size_t)C::kSmemBytes, st, *mx, p);
   b200_timing_mark(B200_TIME_GEMM_W4A16, 1, st);
   b200_count_launches(1);
   return B200_OK;
@@ -1022,22 +916,40 @@ static int launch_gemm_w4(const CUtensorMap* mx, const void* packed, void* y, vo
 // act = 1 (layout 1 only): y [T, N/2] = SiLU(x Wgate) * (x Wup), the LlamaMLP activation (flash_llama_modeling.py:332-335) fused
 // into the projection.  workspace as for b200_gemm_f16 (b200_gemm_workspace_bytes); without it every CTA takes whole
 // super-tiles (no stream-K).
-extern "C" int b200_gemm_w4a16_ex(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
-                                  int groupsize, int layout, int act, void* workspace, void* stream) {
+// splitk != NULL: deferred reduction - nothing is written to y; *splitk describes the fp32 partials left in the workspace.
+static int gemm_w4a16_impl(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K, int groupsize,
+                           int layout, int act, void* workspace, B200SplitK* splitk, void* stream) {
   if (T == 0 || N == 0) return B200_OK;
   if (!w4_check_shape(N, K, groupsize, "gemm_w4a16")) return B200_ERR_ARG;
   const int half_tiles = w4_half_tiles(N, layout, "gemm_w4a16");
   if (half_tiles < 0) return B200_ERR_ARG;
   if (act != 0 && (act != 1 || layout != 1)) { b200_set_last_error("gemm_w4a16: act = 1 needs the gate|up layout"); return B200_ERR_ARG; }
+  const bool defer = splitk != nullptr;
+  if (defer && (!workspace || T > 128)) {
+    b200_set_last_error("gemm_w4a16_deferred: needs a workspace and T <= 128 (one token tile)");
+    return B200_ERR_UNSUPPORTED;
+  }
   const int gr = w4_group_rows(K, &groupsize);
-  const W4Plan pl = launch_plan_w4(T, N, K, num_sms(), workspace != nullptr);
+  const W4Plan pl = launch_plan_w4(T, N, K, num_sms(), workspace != nullptr, defer);
   const CUtensorMap* mx = get_tmap_2d(x, T, K, K, pl.TN, 64, TmapDtype::kF16, TmapSwizzle::k128B);
   if (!mx) return B200_ERR_CUDA;
+  if (defer) {
+    splitk->partial = (const float*)((const char*)workspace + kW4CounterBytes);
+    splitk->bias = bias;
+    splitk->tiles_per_unit = kW4R;
+    splitk->tn = pl.TN;
+    splitk->nkb = pl.nkb;
+    splitk->units_per_cta = pl.su_per_cta;
+    splitk->max_contrib = pl.max_contrib;
+    splitk->half_tiles = half_tiles;
+    splitk->N = (int32_t)N;
+    splitk->T = (int32_t)T;
+  }
   cudaStream_t st = (cudaStream_t)stream;
-#define W4_DISPATCH(TNV)                                                                                                    \
-  (gr == 1 ? launch_gemm_w4<TNV, 1>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, st)                \
-           : gr == 2 ? launch_gemm_w4<TNV, 2>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, st)      \
-                     : launch_gemm_w4<TNV, 4>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, st))
+#define W4_DISPATCH(TNV)                                                                                                           \
+  (gr == 1 ? launch_gemm_w4<TNV, 1>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, defer ? 1 : 0, st)          \
+           : gr == 2 ? launch_gemm_w4<TNV, 2>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, defer ? 1 : 0, st) \
+                     : launch_gemm_w4<TNV, 4>(mx, packed, y, workspace, bias, (int)T, (int)N, pl, half_tiles, act, defer ? 1 : 0, st))
   switch (pl.TN) {
     case 16: return W4_DISPATCH(16);
     case 32: return W4_DISPATCH(32);
@@ -1046,7 +958,20 @@ extern "C" int b200_gemm_w4a16_ex(const void* x, const void* packed, const void*
   }
 #undef W4_DISPATCH
 }
+extern "C" int b200_gemm_w4a16_ex(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
+                                  int groupsize, int layout, int act, void* workspace, void* stream) {
+  return gemm_w4a16_impl(x, packed, bias, y, T, N, K, groupsize, layout, act, workspace, nullptr, stream);
+}
 extern "C" int b200_gemm_w4a16(const void* x, const void* packed, const void* bias, void* y, int64_t T, int64_t N, int64_t K,
                                int groupsize, void* workspace, void* stream) {
-  return b200_gemm_w4a16_ex(x, packed, bias, y, T, N, K, groupsize, 0, 0, workspace, stream);
+  return gemm_w4a16_impl(x, packed, bias, y, T, N, K, groupsize, 0, 0, workspace, nullptr, stream);
+}
+// Deferred split-K reduction: the GEMM leaves fp32 partials in `workspace` and fills *splitk; the next kernel of the stream
+// (b200_rmsnorm_residual_splitk, b200_rope_kv_write_paged_splitk, b200_splitk_silu_mul, b200_splitk_reduce, the fused all-reduce)
+// sums them in contributor order - bit-identical to b200_gemm_w4a16_ex's own fix-up, without its grid-wide wait.  The bias is
+// applied by the consumer.  T <= 128.
+extern "C" int b200_gemm_w4a16_deferred(const void* x, const void* packed, const void* bias, int64_t T, int64_t N, int64_t K,
+                                        int groupsize, int layout, void* workspace, B200SplitK* splitk, void* stream) {
+  if (!splitk) { b200_set_last_error("gemm_w4a16_deferred: splitk is NULL"); return B200_ERR_ARG; }
+  return gemm_w4a16_impl(x, packed, bias, nullptr, T, N, K, groupsize, layout, 0, workspace, splitk, stream);
 }

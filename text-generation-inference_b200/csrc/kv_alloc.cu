@@ -11,6 +11,7 @@
 
 struct B200KvAllocator {
   std::vector<int32_t> free_list;
+  std::vector<uint8_t> in_use;  // per block: handed out and not yet released
   int32_t num_blocks;
   std::mutex mu;
 };
@@ -20,6 +21,7 @@ extern "C" void* b200_kv_alloc_create(int32_t num_blocks) {
   auto* a = new B200KvAllocator();
   a->num_blocks = num_blocks;
   a->free_list.reserve(num_blocks);
+  a->in_use.assign(num_blocks, 0);
   for (int32_t i = num_blocks - 1; i >= 0; --i) a->free_list.push_back(i);  // block 0 is handed out first
   return a;
 }
@@ -43,6 +45,7 @@ extern "C" int b200_kv_alloc_take(void* h, int32_t n, int32_t* out_ids /* host *
   for (int32_t i = 0; i < n; ++i) {
     out_ids[i] = a->free_list.back();
     a->free_list.pop_back();
+    a->in_use[out_ids[i]] = 1;
   }
   return B200_OK;
 }
@@ -50,11 +53,20 @@ extern "C" int b200_kv_alloc_take(void* h, int32_t n, int32_t* out_ids /* host *
 extern "C" int b200_kv_alloc_release(void* h, const int32_t* ids /* host */, int32_t n) {
   auto* a = static_cast<B200KvAllocator*>(h);
   std::lock_guard<std::mutex> lock(a->mu);
+  // validate everything before touching the list: a bad call leaves the allocator unchanged
   for (int32_t i = 0; i < n; ++i) {
     if (ids[i] < 0 || ids[i] >= a->num_blocks) { b200_set_last_error("kv_alloc_release: bad block id"); return B200_ERR_ARG; }
+    if (a->in_use[ids[i]] != 1) {  // free already, or listed twice in this call (marked 2 below)
+      for (int32_t j = 0; j < i; ++j) a->in_use[ids[j]] = 1;
+      b200_set_last_error("kv_alloc_release: double free");
+      return B200_ERR_ARG;
+    }
+    a->in_use[ids[i]] = 2;
+  }
+  for (int32_t i = 0; i < n; ++i) {
+    a->in_use[ids[i]] = 0;
     a->free_list.push_back(ids[i]);
   }
-  if ((int32_t)a->free_list.size() > a->num_blocks) { b200_set_last_error("kv_alloc_release: double free"); return B200_ERR_ARG; }
   return B200_OK;
 }
 

@@ -21,6 +21,7 @@
 // used at e - 1) after every peer signalled epoch e, i.e. after every peer finished reading epoch e - 1.
 // The epoch lives in device memory and is advanced by the kernel itself, so the launch is CUDA-graph replayable.
 #include "common.cuh"
+#include "splitk.cuh"
 #include "../../include/b200_tgis.h"
 
 #include <cstring>
@@ -31,11 +32,16 @@ constexpr int kP2PBlocks = 64;
 constexpr int kP2PThreads = 512;
 constexpr int kP2PMaxWorld = 8;
 constexpr int kP2PChunkBytes = kP2PThreads * 16;  // one 16-byte vector per thread
-constexpr int kP2PHeaderBytes = 4096;
+constexpr int kP2PMaxRows = 256;  // fused all-reduce + norm: one block per token row
+// header: [kP2PMaxRows][kP2PMaxWorld] u32 arrival flags (the chunked kernel uses the first kP2PBlocks rows) | [kP2PMaxRows] u32 epochs
+constexpr int kP2PHeaderBytes = 16384;
+static_assert(kP2PMaxRows * kP2PMaxWorld * 4 + kP2PMaxRows * 4 <= kP2PHeaderBytes, "p2p header");
 constexpr unsigned long long kP2PSpinNs = 4000000000ull;  // a peer that is 4 s late is gone: trap instead of hanging the GPU
 
 struct P2PContext {
   int world = 0, rank = 0;
+  int family = 0;  // 0 unused yet, 1 chunked all-reduce, 2 fused row kernel: a window serves one kernel family (its slot / epoch
+                   // bookkeeping is per block index and the two families cut the message differently)
   int64_t max_bytes = 0;
   unsigned char* window = nullptr;                   // local, cudaMalloc
   unsigned char* peer[kP2PMaxWorld] = {};            // every rank's window mapped here (peer[rank] == window)
@@ -80,7 +86,7 @@ p2p_allreduce_f16_kernel(unsigned char* const* __restrict__ peers, __half* __res
   const int blk = blockIdx.x;
   unsigned char* mine = peers[rank];
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(mine) + blk * kP2PMaxWorld;
-  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(mine) + kP2PBlocks * kP2PMaxWorld + blk;
+  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(mine) + kP2PMaxRows * kP2PMaxWorld + blk;
   pdl_wait();  // `data` is the previous kernel's output; the epoch was written by the previous all-reduce of the stream
   if (threadIdx.x == 0) s_epoch = *my_epoch + 1;
   __syncthreads();
@@ -123,6 +129,229 @@ p2p_allreduce_f16_kernel(unsigned char* const* __restrict__ peers, __half* __res
     }
   }
   if (threadIdx.x == 0) *my_epoch = epoch;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused tensor-parallel layer boundary: all-reduce + residual add + RMSNorm in ONE kernel (decode-sized T).
+//
+// Replaces, per half-layer of the sharded Llama graph, three things of the reference: the row-parallel linear's
+// torch.distributed.all_reduce (utils/layers.py:318-322), and the fused residual + RMSNorm that consumes its result
+// (flash_llama_modeling.py:132-148) - and, when the row-parallel GEMM ran with deferred split-K reduction, the GEMM's own
+// cross-CTA fix-up as well: the rank-partial row is summed from the fp32 partials straight into the NVLink window.
+// One block per token row t:
+//   1. local rank-partial row (fp16 input, or sum of split-K partials rounded to fp16) -> local window, slot = epoch & 1
+//   2. system-scope fence, then the row's flag in every peer's window <- epoch (st.release.sys over NVLink)
+//   3. wait for every peer's flag for this row (ld.acquire.sys, bounded)
+//   4. read the row from every rank's window in rank order, fp32 accumulation, ONE rounding to fp16 = the all-reduced
+//      hidden state (bit-identical on every rank); x = that + residual (fp32) -> residual_out; RMSNorm -> normed_out
+// Same two-slot / per-index epoch protocol as the chunked kernel above (a row only races with itself), graph-replayable.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool kSplitK>
+__global__ void __launch_bounds__(kP2PThreads, 1)
+p2p_allreduce_rmsnorm_kernel(unsigned char* const* __restrict__ peers, const __half* __restrict__ h, const B200SplitK parts,
+                             const __half* __restrict__ residual, const __half* __restrict__ gamma, __half* __restrict__ normed,
+                             __half* __restrict__ res_out, int H, float eps, int world, int rank, int64_t slot_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of the row after the residual add
+  __shared__ float red[32];
+  __shared__ uint32_t s_epoch;
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  unsigned char* mine = peers[rank];
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(mine) + row * kP2PMaxWorld;
+  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(mine) + kP2PMaxRows * kP2PMaxWorld + row;
+  pdl_wait();  // the input is the previous kernel's output; the epoch was written by the previous fused launch of the stream
+  if (threadIdx.x == 0) s_epoch = *my_epoch + 1;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const int64_t row_off = kP2PHeaderBytes + (int64_t)(epoch & 1) * slot_bytes + (int64_t)row * H * 2;
+
+  // 1. rank-partial row -> local window
+  for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
+    uint4 v;
+    if constexpr (kSplitK) {
+      const float4 a = splitk_sum4(parts, row, i), b = splitk_sum4(parts, row, i + 4);
+      v.x = pack_half2(a.x, a.y);
+      v.y = pack_half2(a.z, a.w);
+      v.z = pack_half2(b.x, b.y);
+      v.w = pack_half2(b.z, b.w);
+    } else {
+      v = *reinterpret_cast<const uint4*>(h + (size_t)row * H + i);
+    }
+    *reinterpret_cast<uint4*>(mine + row_off + (int64_t)i * 2) = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. tell every peer, 3. wait for every peer
+  if (threadIdx.x < world && threadIdx.x != rank) {
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(peers[threadIdx.x]) + row * kP2PMaxWorld + rank;
+    st_release_sys(theirs, epoch);
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - epoch) < 0) {
+      if (global_timer_ns() - t0 > kP2PSpinNs) __trap();
+    }
+  }
+  __syncthreads();
+  // 4. sum in rank order, residual add, statistics
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint4 ld[kP2PMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+      if (r < world) ld[r] = ld_peer_v4(peers[r] + row_off + (int64_t)i * 2);  // all peer loads in flight together
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+      if (r < world) add_h8(acc, ld[r]);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __half2float(__float2half_rn(acc[j]));  // the all-reduce result is an fp16 tensor
+    uint4 ov;
+    __half2* o2 = reinterpret_cast<__half2*>(&ov);
+    if (residual) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(residual + (size_t)row * H + i);
+      const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(r2[j]);
+        x[2 * j] += f.x;
+        x[2 * j + 1] += f.y;
+      }
+    }
+    // residual == NULL (first layer, flash_llama_modeling.py:149-150): residual_out = the reduced hidden state itself
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+    *reinterpret_cast<uint4*>(res_out + (size_t)row * H + i) = ov;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xs[i + j] = x[j];
+      ss += x[j] * x[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane_id() == 0) red[warp_id()] = ss;
+  __syncthreads();
+  if (warp_id() == 0) {
+    float v = lane_id() < kP2PThreads / 32 ? red[lane_id()] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float rstd = rsqrtf(red[0] / (float)H + eps);
+  for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
+    const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
+    const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+    uint4 ov;
+    __half2* o2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 g = __half22float2(g2[j]);
+      o2[j] = __floats2half2_rn(xs[i + 2 * j] * rstd * g.x, xs[i + 2 * j + 1] * rstd * g.y);
+    }
+    *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = ov;
+  }
+  if (threadIdx.x == 0) *my_epoch = epoch;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-parallel greedy head without the logits all-gather (replaces TensorParallelHead's
+// all_gather_into_tensor of [T, V/tp] fp16 per rank, utils/layers.py:249-269, followed by Greedy's argmax, utils/tokens.py:44-46,
+// for all-greedy batches): every rank takes the arg-max of its own vocabulary shard, the (value, index) pairs cross NVLink
+// (8 bytes per row and rank instead of V/tp logits), and every rank picks the same winner: the largest value, ties to the
+// lowest global token id - exactly torch.argmax over the concatenated row.  One block per row, window family 3:
+// slot layout [2][kP2PMaxRows][2] u32 (value bits, global index).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kP2PArgmaxThreads = 1024;
+__global__ void __launch_bounds__(kP2PArgmaxThreads, 1)
+p2p_argmax_kernel(unsigned char* const* __restrict__ peers, const __half* __restrict__ logits, int64_t V_local, int64_t ld,
+                  const int64_t* __restrict__ banned, int64_t* __restrict__ out, int world, int rank) {
+  __shared__ float sv[kP2PArgmaxThreads / 32];
+  __shared__ int si[kP2PArgmaxThreads / 32];
+  __shared__ uint32_t s_epoch;
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  unsigned char* mine = peers[rank];
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(mine) + row * kP2PMaxWorld;
+  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(mine) + kP2PMaxRows * kP2PMaxWorld + row;
+  pdl_wait();
+  if (threadIdx.x == 0) s_epoch = *my_epoch + 1;
+  // local arg-max over this rank's shard (first index wins ties); the banned token id is global
+  const __half* lrow = logits + (size_t)row * ld;
+  const int64_t v0 = (int64_t)rank * V_local;
+  const int ban = banned ? (int)(banned[row] - v0) : -1;  // negative or >= V_local: not in this shard
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  const bool vec = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int V8 = vec ? (int)(V_local & ~7LL) : 0;
+  for (int i = threadIdx.x * 8; i < V8; i += kP2PArgmaxThreads * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(lrow + i);
+    const __half* hv = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = (i + j == ban) ? -INFINITY : __half2float(hv[j]);
+      if (f > best) { best = f; best_i = i + j; }
+    }
+  }
+  for (int i = V8 + threadIdx.x; i < (int)V_local; i += kP2PArgmaxThreads) {
+    const float f = (i == ban) ? -INFINITY : __half2float(lrow[i]);
+    if (f > best || (f == best && i < best_i)) { best = f; best_i = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if (lane_id() == 0) { sv[warp_id()] = best; si[warp_id()] = best_i; }
+  __syncthreads();
+  if (warp_id() == 0) {
+    best = sv[lane_id()];
+    best_i = si[lane_id()];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    const uint32_t epoch = s_epoch;
+    const int64_t slot_off = kP2PHeaderBytes + (int64_t)(epoch & 1) * (kP2PMaxRows * 8) + (int64_t)row * 8;
+    if (lane_id() == 0) {
+      // an all -inf / all-banned shard still takes part with (-inf, its first index)
+      const uint32_t gi = (uint32_t)(v0 + (best_i == 0x7fffffff ? 0 : best_i));
+      *reinterpret_cast<uint2*>(mine + slot_off) = make_uint2(__float_as_uint(best), gi);
+      __threadfence_system();
+    }
+    __syncwarp();
+    if (lane_id() < world && lane_id() != rank) {
+      uint32_t* theirs = reinterpret_cast<uint32_t*>(peers[lane_id()]) + row * kP2PMaxWorld + rank;
+      st_release_sys(theirs, epoch);
+      const unsigned long long t0 = global_timer_ns();
+      while ((int32_t)(ld_acquire_sys(my_flags + lane_id()) - epoch) < 0) {
+        if (global_timer_ns() - t0 > kP2PSpinNs) __trap();
+      }
+    }
+    __syncwarp();
+    float wv = -INFINITY;
+    uint32_t wi = 0xffffffffu;
+    if (lane_id() < world) {
+      uint2 pr;
+      asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(pr.x), "=r"(pr.y) : "l"(peers[lane_id()] + slot_off) : "memory");
+      wv = __uint_as_float(pr.x);
+      wi = pr.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {  // world <= 8 lanes hold candidates
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+    }
+    if (lane_id() == 0) {
+      out[row] = (int64_t)wi;
+      *my_epoch = epoch;
+    }
+  }
 }
 
 }  // namespace b200
@@ -194,10 +423,84 @@ extern "C" int b200_p2p_allreduce_f16(void* ctx_, void* data, int64_t n, void* s
   }
   for (int r = 0; r < ctx->world; ++r)
     if (!ctx->peer[r]) { b200_set_last_error("p2p_allreduce: b200_p2p_connect has not run"); return B200_ERR_ARG; }
+  if (ctx->family == 2) { b200_set_last_error("p2p_allreduce: this window already serves b200_p2p_allreduce_rmsnorm"); return B200_ERR_ARG; }
+  ctx->family = 1;
   const int64_t n_chunks = (n * 2 + kP2PChunkBytes - 1) / kP2PChunkBytes;
   const int blocks = (int)(n_chunks < kP2PBlocks ? n_chunks : kP2PBlocks);
   B200_LAUNCH(p2p_allreduce_f16_kernel, dim3(blocks), dim3(kP2PThreads), 0, (cudaStream_t)stream,
               (unsigned char* const*)ctx->peer_table, (__half*)data, n, ctx->world, ctx->rank, ctx->max_bytes);
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+// Fused layer boundary (see the kernel).  Exactly one of h (fp16 [T, H], this rank's partial sums) and h_parts (a deferred
+// row-parallel GEMM, H = h_parts->N, T = h_parts->T) is given.  residual may be NULL (first layer): residual_out then receives
+// the reduced hidden state.  T <= 256, T * H * 2 <= max_bytes, H % 8 == 0, H <= 16384.
+extern "C" int b200_p2p_allreduce_rmsnorm(void* ctx_, const void* h, const B200SplitK* h_parts, const void* residual, const void* gamma,
+                                          void* normed_out, void* residual_out, int64_t T, int64_t H, float eps, void* stream) {
+  P2PContext* ctx = (P2PContext*)ctx_;
+  if (!ctx || (!h) == (!h_parts) || !gamma || !normed_out || !residual_out) {
+    b200_set_last_error("p2p_allreduce_rmsnorm: need a context, exactly one of h / h_parts, gamma and both outputs");
+    return B200_ERR_ARG;
+  }
+  if (h_parts) {
+    if (!h_parts->partial || h_parts->half_tiles != 0 || h_parts->T <= 0 || h_parts->T > h_parts->tn) {
+      b200_set_last_error("p2p_allreduce_rmsnorm: h_parts is not a plain-layout B200SplitK");
+      return B200_ERR_ARG;
+    }
+    T = h_parts->T;
+    H = h_parts->N;
+  }
+  if (T == 0) return B200_OK;
+  if (T > kP2PMaxRows || H % 8 != 0 || H > 16384 || T * H * 2 > ctx->max_bytes || (h && ((uintptr_t)h & 15) != 0)) {
+    b200_set_last_error("p2p_allreduce_rmsnorm: need T <= 256, H % 8 == 0, H <= 16384, T * H * 2 <= max_bytes, 16-byte aligned h");
+    return B200_ERR_ARG;
+  }
+  for (int r = 0; r < ctx->world; ++r)
+    if (!ctx->peer[r]) { b200_set_last_error("p2p_allreduce_rmsnorm: b200_p2p_connect has not run"); return B200_ERR_ARG; }
+  if (ctx->family == 1) { b200_set_last_error("p2p_allreduce_rmsnorm: this window already serves b200_p2p_allreduce_f16"); return B200_ERR_ARG; }
+  ctx->family = 2;
+  const size_t smem = (size_t)H * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h_parts) {
+    constexpr auto kernel = p2p_allreduce_rmsnorm_kernel<true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel<splitk>", kernel, dim3((unsigned)T), dim3(kP2PThreads), smem, st,
+                   (unsigned char* const*)ctx->peer_table, (const __half*)nullptr, *h_parts, (const __half*)residual, (const __half*)gamma,
+                   (__half*)normed_out, (__half*)residual_out, (int)H, eps, ctx->world, ctx->rank, ctx->max_bytes);
+  } else {
+    constexpr auto kernel = p2p_allreduce_rmsnorm_kernel<false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel", kernel, dim3((unsigned)T), dim3(kP2PThreads), smem, st,
+                   (unsigned char* const*)ctx->peer_table, (const __half*)h, B200SplitK{}, (const __half*)residual, (const __half*)gamma,
+                   (__half*)normed_out, (__half*)residual_out, (int)H, eps, ctx->world, ctx->rank, ctx->max_bytes);
+  }
+  b200_count_launches(1);
+  return B200_OK;
+}
+
+// Greedy ids of a vocabulary-sharded head (see the kernel): logits [B, V_local] fp16 with row stride ld (halves), this rank's
+// shard = global token ids [rank * V_local, (rank + 1) * V_local); banned_ids (optional, [B]) as in b200_argmax, global ids.
+// out_ids [B] int64 is identical on every rank.  B <= 256.  The window (b200_p2p_create with any max_bytes >= 4096) must not
+// be shared with the other p2p kernels.
+extern "C" int b200_p2p_argmax(void* ctx_, const void* logits, int64_t* out_ids, int64_t B, int64_t V_local, int64_t ld,
+                               const int64_t* banned_ids, void* stream) {
+  P2PContext* ctx = (P2PContext*)ctx_;
+  if (!ctx || !logits || !out_ids || B < 0 || V_local <= 0 || ld < V_local) {
+    b200_set_last_error("p2p_argmax: null argument or bad shape");
+    return B200_ERR_ARG;
+  }
+  if (B == 0) return B200_OK;
+  if (B > kP2PMaxRows || 2 * ctx->max_bytes < 2 * kP2PMaxRows * 8 || V_local * ctx->world > 0x7fffffffLL) {
+    b200_set_last_error("p2p_argmax: need B <= 256 and a window of at least 4096 bytes");
+    return B200_ERR_ARG;
+  }
+  for (int r = 0; r < ctx->world; ++r)
+    if (!ctx->peer[r]) { b200_set_last_error("p2p_argmax: b200_p2p_connect has not run"); return B200_ERR_ARG; }
+  if (ctx->family != 0 && ctx->family != 3) { b200_set_last_error("p2p_argmax: this window already serves another p2p kernel"); return B200_ERR_ARG; }
+  ctx->family = 3;
+  B200_LAUNCH(p2p_argmax_kernel, dim3((unsigned)B), dim3(kP2PArgmaxThreads), 0, (cudaStream_t)stream,
+              (unsigned char* const*)ctx->peer_table, (const __half*)logits, V_local, ld, banned_ids, out_ids, ctx->world, ctx->rank);
   b200_count_launches(1);
   return B200_OK;
 }

@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <map>
 #include <mutex>
+#include <cstring>
 #include <string>
 #include <tuple>
 
@@ -141,4 +142,44 @@ void b200_timing_mark(int which, int is_stop, cudaStream_t st) {
   if (!t || t->which != which || t->used + (is_stop ? 0 : 2) > (int)t->ev.size()) return;
   if (!is_stop) { cudaEventRecord(t->ev[t->used], st); }
   else if (t->used + 1 < (int)t->ev.size()) { cudaEventRecord(t->ev[t->used + 1], st); t->used += 2; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Step trace (debug): while a device buffer is attached, every B200_LAUNCH is followed by a one-thread kernel that
+// stores %globaltimer into the next slot.  Consecutive differences = device time of each kernel including its launch gap,
+// in stream order, L2 state as in production; the launch sequence can be captured into a CUDA graph and replayed.
+// ---------------------------------------------------------------------------------------------------------
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_cap = 0, g_trace_n = 0;
+static std::string g_trace_names;
+
+__global__ void b200_stamp_kernel(unsigned long long* out) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *out = t;
+}
+
+// device_buf: capacity uint64 slots (NULL detaches).  Slot 0 is stamped by b200_debug_step_trace_begin.
+extern "C" void b200_debug_step_trace(void* device_buf, int capacity) {
+  g_trace_buf = static_cast<unsigned long long*>(device_buf);
+  g_trace_cap = device_buf ? capacity : 0;
+  g_trace_n = 0;
+  g_trace_names.clear();
+}
+extern "C" void b200_debug_step_trace_begin(void* stream) { b200_step_trace_stamp("<begin>", (cudaStream_t)stream); }
+// newline-separated kernel names of the stamped launches so far, in order; returns how many
+extern "C" int b200_debug_step_trace_names(char* out, int64_t cap) {
+  if (out && cap > 0) {
+    const size_t n = g_trace_names.size() < (size_t)cap - 1 ? g_trace_names.size() : (size_t)cap - 1;
+    memcpy(out, g_trace_names.data(), n);
+    out[n] = 0;
+  }
+  return g_trace_n;
+}
+void b200_step_trace_stamp(const char* kernel_name, cudaStream_t stream) {
+  if (!g_trace_buf || g_trace_n >= g_trace_cap) return;
+  b200_stamp_kernel<<<1, 1, 0, stream>>>(g_trace_buf + g_trace_n);
+  ++g_trace_n;
+  g_trace_names += kernel_name;
+  g_trace_names += '\n';
 }

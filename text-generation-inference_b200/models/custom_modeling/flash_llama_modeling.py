@@ -30,7 +30,7 @@ from ...utils.layers import (
     TensorParallelRowLinear,
 )
 from ...utils.gptq.exllamav2 import Ex4bitLinearV2
-from ...utils.p2p import LayerBoundaryAllReduce
+from ...utils.p2p import FusedBoundary, LayerBoundaryAllReduce
 from ...utils.paged import PagedKVCacheManager, PagedKVState
 
 
@@ -189,7 +189,11 @@ class FlashLlamaForCausalLM(nn.Module):
         self.kv_cache_manager: Optional[PagedKVCacheManager] = None
         self._cw = None
         self.scratch = StepScratch(self)
-        self._all_reduce = LayerBoundaryAllReduce(self.process_group)  # NCCL unless B200_P2P_ALLREDUCE=1 (utils/p2p.py)
+        # the layer boundary: inside the C++ step over NVLink peer memory at decode sizes (FusedBoundary), NCCL / the one-shot
+        # all-reduce between the half-layer block calls otherwise (prefill); B200_P2P_ALLREDUCE=0 keeps everything on NCCL
+        self._all_reduce = LayerBoundaryAllReduce(self.process_group)
+        self._boundary = FusedBoundary(self.process_group, config.hidden_size)
+        self.defer_splitk = __import__("os").environ.get("B200_DEFER_SPLITK", "1") != "0"
 
     def get_input_embeddings(self) -> nn.Module:
         return self.model.embed_tokens
@@ -271,7 +275,14 @@ class FlashLlamaForCausalLM(nn.Module):
             s.head_rows, s.n_head_rows = head_rows.data_ptr(), head_rows.shape[0]
         s.logits = logits.data_ptr()
         s.next_ids = next_ids.data_ptr() if next_ids is not None else None
+        s.defer_splitk = int(self.defer_splitk)
+        s.p2p_norm, s.p2p_argmax = self._boundary.norm, self._boundary.argmax
         return s
+
+    @property
+    def greedy_ids_in_step(self) -> bool:
+        """the step can produce the greedy ids itself: single rank, or a sharded head with the (value, index) exchange"""
+        return self.model.tp_world_size == 1 or (self._boundary.argmax is not None and self.lm_head.should_gather)
 
     def run_step(self, s: _lib.B200LlamaStep, embed: bool = True) -> None:
         """Enqueues the step on the current stream: one C call single-rank; per half-layer + NCCL when sharded."""
@@ -279,7 +290,8 @@ class FlashLlamaForCausalLM(nn.Module):
         w = self._cw
         st = torch.cuda.current_stream().cuda_stream
         tp = self.model.tp_world_size
-        if tp == 1 and embed:
+        if embed and (tp == 1 or (s.p2p_norm and s.T <= FusedBoundary.MAX_ROWS)):
+            # one C call for the whole step; when sharded the layer boundary runs inside it over NVLink peer memory
             _lib.check(lib.b200_llama_step(ctypes.byref(w), ctypes.byref(s), st), "llama_step")
             return
         hidden = self.scratch.bufs["hidden"][:s.T]

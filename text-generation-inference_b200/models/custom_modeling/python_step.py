@@ -8,8 +8,9 @@
    logits and the arg-max ids into the caller's buffers, the ids chain on the device, and from the third step of a stable
    batch the whole step is replayed as a CUDA graph.  FlashLlama implements the protocol with the C++ step runtime
    (csrc/llama_step.cu); `PythonFusedGreedy` implements it by enqueuing the family's ordinary decode forward, whose torch
-   temporaries then come from the graph's private pool.  EXPERIMENTAL: off unless B200_PY_FUSED_STEP=1 (or B200_NEOX_FUSED=1,
-   the first spelling), not validated on a GPU yet.
+   temporaries then come from the graph's private pool.  On by default on a single rank (validated on B200 for GPT-NeoX and
+   Santacoder, round 2); sharded models take it with B200_PY_FUSED_STEP=1 only (NCCL inside the captured graph), and
+   B200_PY_FUSED_STEP=0 turns it off.
 """
 from __future__ import annotations
 
@@ -48,15 +49,17 @@ class _NoScratch:
     version = 0  # FlashCausalLM keys its cached step on this; nothing here is ever re-allocated
 
 
-def _enabled() -> bool:
-    return os.environ.get("B200_PY_FUSED_STEP", "0") == "1" or os.environ.get("B200_NEOX_FUSED", "0") == "1"
-
-
 class PythonFusedGreedy:
-    """Mixin for a `...ForCausalLM` module: needs `self.model` (the backbone, called like the reference's forward) and
-    `self.lm_head` (a TensorParallelHead)."""
-    fused_greedy_enabled = _enabled()
+    """Mixin for a `...ForCausalLM` module: needs `self.model` (the backbone, called like the reference's forward),
+    `self.lm_head` (a TensorParallelHead) and `self.process_group`."""
     scratch = _NoScratch()
+
+    @property
+    def fused_greedy_enabled(self) -> bool:
+        switch = os.environ.get("B200_PY_FUSED_STEP", "")
+        if switch == "0":
+            return False
+        return switch == "1" or self.process_group.size() == 1
 
     def make_step(self, *, T: int, B: int, is_prefill: bool, max_s: int, input_ids, position_ids, kv: PagedKVState,
                   cu_seqlens=None, head_rows=None, logits=None, next_ids=None, inputs_embeds=None) -> PythonStep:

@@ -317,13 +317,15 @@ class FlashCausalLM(Model):
                       banned=torch.full((B,), -1, dtype=torch.int64, device=self.device), banned_host=[-1] * B,
                       steps=0, graph=None, max_s_cap=0)
             tp = getattr(self.engine, "world_size", 1)
+            in_step = tp == 1 or getattr(self.model, "greedy_ids_in_step", False)
+            st["ids_in_step"] = in_step
             st["step"] = self.model.make_step(T=B, B=B, is_prefill=False, max_s=max(batch.total_lengths), input_ids=batch.input_ids,
                                               position_ids=batch.position_ids, kv=kv, logits=st["logits"],
-                                              next_ids=st["next_ids"] if tp == 1 else None)
+                                              next_ids=st["next_ids"] if in_step else None)
             st["step"].banned_ids = st["banned"].data_ptr()
             if hasattr(st["step"], "banned"):  # Python step objects (NeoxStep) take the tensor itself
                 st["step"].banned = st["banned"]
-            if tp > 1 and self.model.lm_head.should_gather:
+            if tp > 1 and not in_step and self.model.lm_head.should_gather:
                 # vocab-sharded head: all-gather the [B, V/tp] logits (utils/layers.py:249-269), then one arg-max
                 st["gathered"] = torch.empty(tp, B, V, dtype=torch.float16, device=self.device)
                 st["full"] = torch.empty(B, tp * V, dtype=torch.float16, device=self.device)
@@ -367,7 +369,7 @@ class FlashCausalLM(Model):
                 kv.block_table.data_ptr(), kv.block_table.stride(0), kv.context_lens.data_ptr(), batch.position_ids.data_ptr(),
                 kv.slot_mapping.data_ptr(), None, None, B, stream), "decode_advance")
             self.model.run_step(s)
-            if getattr(self.engine, "world_size", 1) > 1:
+            if getattr(self.engine, "world_size", 1) > 1 and not st.get("ids_in_step", False):
                 from .. import ops
                 if "gathered" in st:
                     torch.distributed.all_gather_into_tensor(st["gathered"], st["logits"], group=self.model.process_group)

@@ -252,6 +252,91 @@ def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, N: int, groupsize: int, bi
 
 
 # ------------------------------------------------------------------------------------------------------
+# Deferred split-K reduction (include/b200_tgis.h "B200SplitK"): the GEMM leaves fp32 partials in the workspace and the
+# next kernel on the stream sums them.  The returned SplitK keeps the workspace alive; it is valid until the next GEMM
+# that uses the same workspace.
+# ------------------------------------------------------------------------------------------------------
+class SplitK:
+    def __init__(self, desc: "_lib.B200SplitK", workspace: torch.Tensor, bias: Optional[torch.Tensor]):
+        self.desc, self.workspace, self.bias = desc, workspace, bias
+
+    @property
+    def ref(self):
+        import ctypes
+        return ctypes.byref(self.desc)
+
+    @property
+    def shape(self):
+        return self.desc.T, self.desc.N
+
+
+def gemm_w4a16_deferred(x: torch.Tensor, packed: torch.Tensor, N: int, groupsize: int, bias: Optional[torch.Tensor] = None,
+                        workspace: Optional[torch.Tensor] = None, layout: int = W4_LAYOUT_PLAIN) -> SplitK:
+    _req(x, torch.float16, "x")
+    _req(packed, torch.uint8, "packed")
+    assert x.is_contiguous() and packed.is_contiguous()
+    T, K = x.shape
+    if workspace is None:
+        workspace = gemm_workspace(x.device, T, N, K)
+    desc = _lib.B200SplitK()
+    import ctypes
+    _lib.check(_lib.load().b200_gemm_w4a16_deferred(_ptr(x), _ptr(packed), _ptr(bias), T, N, K, groupsize, layout, _ptr(workspace),
+                                                    ctypes.byref(desc), _stream()), "gemm_w4a16_deferred")
+    return SplitK(desc, workspace, bias)
+
+
+def gemm_f16_deferred(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                      workspace: Optional[torch.Tensor] = None) -> SplitK:
+    _req(x, torch.float16, "x")
+    _req(w, torch.float16, "w")
+    assert x.is_contiguous() and w.is_contiguous()
+    T, K = x.shape
+    N = w.shape[0]
+    if workspace is None:
+        workspace = gemm_workspace(x.device, T, N, K)
+    desc = _lib.B200SplitK()
+    import ctypes
+    _lib.check(_lib.load().b200_gemm_f16_deferred(_ptr(x), _ptr(w), _ptr(bias), T, N, K, _ptr(workspace), ctypes.byref(desc),
+                                                  _stream()), "gemm_f16_deferred")
+    return SplitK(desc, workspace, bias)
+
+
+def splitk_reduce(parts: SplitK) -> torch.Tensor:
+    T, N = parts.shape
+    y = torch.empty(T, N, dtype=torch.float16, device=parts.workspace.device)
+    _lib.check(_lib.load().b200_splitk_reduce(parts.ref, _ptr(y), _stream()), "splitk_reduce")
+    return y
+
+
+def rmsnorm_residual_splitk(parts: SplitK, residual: torch.Tensor, gamma: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    _req(residual, torch.float16, "residual")
+    residual = residual.contiguous()
+    normed, res_out = torch.empty_like(residual), torch.empty_like(residual)
+    _lib.check(_lib.load().b200_rmsnorm_residual_splitk(parts.ref, _ptr(residual), _ptr(gamma), _ptr(normed), _ptr(res_out),
+                                                        float(eps), _stream()), "rmsnorm_residual_splitk")
+    return normed, res_out
+
+
+def rope_kv_write_paged_splitk(parts: SplitK, cos: torch.Tensor, sin: torch.Tensor, position_ids: torch.Tensor,
+                               slot_mapping: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, n_heads: int,
+                               n_kv_heads: int, head_dim: int) -> torch.Tensor:
+    """-> qkv [T, (n_heads + 2 n_kv) d] fp16, q and k rotated; k and v also scattered into the pools."""
+    T, N = parts.shape
+    qkv = torch.empty(T, N, dtype=torch.float16, device=parts.workspace.device)
+    _lib.check(_lib.load().b200_rope_kv_write_paged_splitk(parts.ref, _ptr(qkv), _ptr(cos), _ptr(sin), _ptr(position_ids),
+                                                           _ptr(slot_mapping), _ptr(k_pool), _ptr(v_pool), n_heads, n_kv_heads,
+                                                           head_dim, _stream()), "rope_kv_write_paged_splitk")
+    return qkv
+
+
+def splitk_silu_mul(parts: SplitK) -> torch.Tensor:
+    T, N = parts.shape
+    out = torch.empty(T, N // 2, dtype=torch.float16, device=parts.workspace.device)
+    _lib.check(_lib.load().b200_splitk_silu_mul(parts.ref, _ptr(out), _stream()), "splitk_silu_mul")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
 # KV pool helpers (layout documented in DESIGN.md; used by tests and the block manager)
 # ------------------------------------------------------------------------------------------------------
 def kv_pool_alloc(num_blocks: int, n_kv_heads: int, head_dim: int, device) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -1,9 +1,13 @@
-"""All-reduce at the tensor-parallel layer boundary: NCCL, or (B200_P2P_ALLREDUCE=1, experimental) the library's one-shot
-kernel over NVLink peer memory for decode-sized messages (csrc/p2p_allreduce.cu).
+"""The tensor-parallel layer boundary over NVLink peer memory (csrc/p2p_allreduce.cu), with NCCL for what it does not take.
 
 The reference calls `torch.distributed.all_reduce(out, group=self.process_group)` after every row-parallel linear and the
-vocab-parallel embedding (utils/layers.py:303-306, :343-345).  `LayerBoundaryAllReduce` keeps that call as the default and
-as the path for anything the peer-memory kernel does not take (large prefill messages, dtypes other than fp16).
+vocab-parallel embedding (utils/layers.py:303-306, :343-345) and all-gathers the sharded head's logits (:249-269).
+  * `LayerBoundaryAllReduce`: that all-reduce; decode-sized fp16 messages go through the library's one-shot peer-memory kernel,
+    everything else (prefill, other dtypes) through NCCL.
+  * `FusedBoundary`: the windows the C++ step runtime uses to run the whole sharded decode step without a host-side
+    collective: all-reduce + residual + RMSNorm in one kernel (b200_p2p_allreduce_rmsnorm) and the greedy head as a
+    (value, index) exchange (b200_p2p_argmax).
+B200_P2P_ALLREDUCE=0 keeps every collective on NCCL.
 """
 from __future__ import annotations
 
@@ -19,7 +23,37 @@ P2P_MAX_BYTES = 2 << 20  # messages up to 2 MiB (bs 256 x hidden 4096 fp16) go o
 
 
 def p2p_requested() -> bool:
-    return os.environ.get("B200_P2P_ALLREDUCE", "0") == "1"
+    return os.environ.get("B200_P2P_ALLREDUCE", "1") != "0"
+
+
+def _open_window(process_group, max_bytes: int):
+    """b200_p2p_create + IPC handle exchange over the group + b200_p2p_connect -> context handle."""
+    lib = _lib.load()
+    world, rank = process_group.size(), process_group.rank()
+    n = lib.b200_p2p_handle_bytes()
+    mine = (ctypes.c_ubyte * n)()
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.b200_p2p_create(max_bytes, world, rank, ctypes.byref(ctx), mine), "p2p_create")
+    local = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
+    gathered = torch.empty(world * n, dtype=torch.uint8, device="cuda")
+    torch.distributed.all_gather_into_tensor(gathered, local, group=process_group)
+    handles = (ctypes.c_ubyte * (world * n)).from_buffer_copy(bytes(gathered.cpu().tolist()))
+    _lib.check(lib.b200_p2p_connect(ctx, handles), "p2p_connect")
+    torch.distributed.barrier(group=process_group)  # every window is mapped everywhere before the first use
+    return ctx
+
+
+class FusedBoundary:
+    """Windows for the in-step layer boundary.  `norm` serves b200_p2p_allreduce_rmsnorm for up to `max_rows` token rows of
+    `hidden_size`; `argmax` serves b200_p2p_argmax.  Both are None when the group has one rank or p2p is switched off."""
+
+    MAX_ROWS = 256
+
+    def __init__(self, process_group, hidden_size: int):
+        self.norm = self.argmax = None
+        if process_group.size() > 1 and p2p_requested() and torch.cuda.is_available():
+            self.norm = _open_window(process_group, self.MAX_ROWS * hidden_size * 2)
+            self.argmax = _open_window(process_group, 8192)
 
 
 class LayerBoundaryAllReduce:
@@ -29,25 +63,12 @@ class LayerBoundaryAllReduce:
         self._ctx = None
         self._max_bytes = 0
         if self.world > 1 and p2p_requested():
-            if not torch.cuda.is_available():
-                raise RuntimeError("B200_P2P_ALLREDUCE=1 needs CUDA devices: the peer-memory all-reduce has no CPU form")
-            self._connect(max_bytes)
+            if torch.cuda.is_available():  # gloo / CPU groups (host-logic tests) stay on torch.distributed
+                self._connect(max_bytes)
 
     def _connect(self, max_bytes: int) -> None:
-        lib = _lib.load()
-        rank = self.process_group.rank()
-        n = lib.b200_p2p_handle_bytes()
-        mine = (ctypes.c_ubyte * n)()
-        ctx = ctypes.c_void_p()
-        _lib.check(lib.b200_p2p_create(max_bytes, self.world, rank, ctypes.byref(ctx), mine), "p2p_create")
-        local = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
-        gathered = torch.empty(self.world * n, dtype=torch.uint8, device="cuda")
-        torch.distributed.all_gather_into_tensor(gathered, local, group=self.process_group)
-        handles = (ctypes.c_ubyte * (self.world * n)).from_buffer_copy(bytes(gathered.cpu().tolist()))
-        _lib.check(lib.b200_p2p_connect(ctx, handles), "p2p_connect")
-        torch.distributed.barrier(group=self.process_group)  # every window is mapped everywhere before the first use
-        self._ctx = ctx
-        self._max_bytes = lib.b200_p2p_max_bytes(ctx)
+        self._ctx = _open_window(self.process_group, max_bytes)
+        self._max_bytes = _lib.load().b200_p2p_max_bytes(self._ctx)
 
     @property
     def uses_peer_memory(self) -> bool:

@@ -117,18 +117,20 @@ class PagedKVCacheManager:
         """Extends existing sequences (or creates new ones when sequence_ids is None) by the given token counts.
         Returns the sequence ids.  `reserve_tokens[i]` additionally pre-books blocks for future tokens so a decode
         loop never has to touch the block table (continuous batching sizes a request by input + max_output)."""
-        if sequence_ids is None:
-            sequence_ids = []
-            for _ in num_tokens_per_sequence:
-                sequence_ids.append(self._next_id)
-                self._blocks[self._next_id] = []
-                self._lens[self._next_id] = 0
-                self._next_id += 1
+        new = sequence_ids is None
+        if new:  # ids are only registered once the blocks are booked: a rejected prefill (OutOfBlocks) leaves no trace
+            sequence_ids = list(range(self._next_id, self._next_id + len(num_tokens_per_sequence)))
         need = []
         for i, (sid, n) in enumerate(zip(sequence_ids, num_tokens_per_sequence)):
-            target = self._lens[sid] + n + (reserve_tokens[i] if reserve_tokens else 0)
-            need.append(max(0, self.blocks_needed(target) - len(self._blocks[sid])))
+            have_len, have_blocks = (0, 0) if new else (self._lens[sid], len(self._blocks[sid]))
+            target = have_len + n + (reserve_tokens[i] if reserve_tokens else 0)
+            need.append(max(0, self.blocks_needed(target) - have_blocks))
         got = self._take(sum(need))  # all or nothing
+        if new:
+            for sid in sequence_ids:
+                self._blocks[sid] = []
+                self._lens[sid] = 0
+            self._next_id += len(sequence_ids)
         pos = 0
         for sid, n, k in zip(sequence_ids, num_tokens_per_sequence, need):
             self._blocks[sid].extend(got[pos:pos + k])
