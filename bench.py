@@ -1,23 +1,28 @@
 #!/usr/bin/env python
 """bench.py — decode throughput of the TGIS continuous-batching hot path on B200 (contract in the task prompt / DESIGN.md).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference] [--no-extra]
 
-Workloads (BASELINE.json configs):
-  llama2-7b-gptq   config[2]: Llama-2-7B GPTQ int4 g128, 1 GPU, bs=64, seq 1024->2048   (default at N=1: the config the
-                   metric "decode tokens/sec/GPU (bs=64, seq 1k->2k)" is quoted on)
-  llama2-7b-fp16   config[3]: Llama-2-7B fp16, tensor parallel over N GPUs, bs=64, 1024->2048 (default at N>1; int4
-                   Llama-2-7B cannot be row-sharded beyond tp=2: 11008/tp is not a multiple of the group size 128)
-  tinyllama-fp16   config[1]: TinyLlama-1.1B fp16, bs=32, 512->1024
-  llama3-8b-gptq   north-star "Llama-8B": Llama-3-8B (GQA-8) GPTQ int4, bs=64, 1024->2048
+Workloads (BASELINE.json):
+  llama3-8b-gptq   the north-star target "batched int4 Llama-8B decode at bs=64": Llama-3-8B (GQA-8) GPTQ int4 g128, bs=64,
+                   seq 1024->2048, tensor parallel over N GPUs.  DEFAULT AT EVERY N: it is the one int4 model that shards at
+                   tp = 1/2/4/8, so the driver's 1/2/4/8 curve compares like with like.
+  llama2-7b-gptq   config[2]: Llama-2-7B GPTQ int4, 1 GPU, bs=64, 1024->2048 (row-sharding stops at tp=2: 11008/tp % 128).
+                   Measured in the same run at N=1 and reported under "extra".
+  llama2-7b-fp16   config[3]: Llama-2-7B fp16, tensor parallel, bs=64.  Measured in the same run at N>1, under "extra".
+  tinyllama-fp16   config[1]: TinyLlama-1.1B fp16, bs=32, 512->1024 (on request).
 
-A "step" is one decode step of the whole batch (one token per sequence).  The timed window is K consecutive steps
-centred on the mean context of the workload (L = (start+end)/2), reached by really running prefill + decode from the
-prompt, so KV contents, block tables and lengths are what the serving path produces.
-  value : B*K / device time of K steps with all inputs resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the public API `FlashCausalLM.generate_token(batch)` driven from host buffers: every step
-          copies the step's input token ids from pinned host memory and reads the chosen ids back to the host
-  roofline : attn_decode_paged kernel, algorithmic KV bytes per launch / CUDA-event time per launch vs measured HBM peak
+A "step" is one decode step of the whole batch (one token per sequence).  The run really generates the whole trajectory
+L0 -> L1 from the prompt, so KV contents, block tables and lengths are what the serving path produces:
+  value : B*K / device time of K consecutive graph-replayed steps centred on the mean context (L0+L1)/2, inputs resident in
+          HBM, no host round trip (CUDA events, max over ranks)
+  e2e   : the same metric over ALL the other decode steps of the trajectory through the public API
+          `FlashCausalLM.generate_token(batch)` driven from host buffers: every step copies the step's input token ids from
+          pinned host memory and reads the chosen ids back to the host
+  roofline : attn_decode_paged kernel, algorithmic KV bytes per launch / CUDA-event time per launch vs the measured HBM peak;
+          "gemm" beside it: the int4 / fp16 linears' weight bytes per step / their CUDA-event time per step
+  self_check : greedy ids of a 2-layer model of the same widths through the same code path vs the CPU oracle (tests' rule:
+          exact outside the 2-ulp tie band)
   cpu_baseline : the reference's CPU CausalLM path (HF eager fp32, padded batch, greedy) on a bounded sample
 `--impl reference` times that CPU path alone (rank 0 only) and prints the same JSON line with "impl": "reference".
 Data is synthetic: seeded random weights of the named architecture, prompts "test " * L0 (the reference's own
@@ -27,6 +32,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -39,12 +45,13 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (arch, quantize, batch, prompt_len, end_len)
+    "llama3-8b-gptq": ("llama-3-8b", "gptq", 64, 1024, 2048),
     "llama2-7b-gptq": ("llama-2-7b", "gptq", 64, 1024, 2048),
     "llama2-7b-fp16": ("llama-2-7b", None, 64, 1024, 2048),
     "tinyllama-fp16": ("tinyllama-1.1b", None, 32, 512, 1024),
-    "llama3-8b-gptq": ("llama-3-8b", "gptq", 64, 1024, 2048),
     "tiny-test": ("tiny-test", None, 4, 32, 256),
 }
+DEFAULT_WORKLOAD = "llama3-8b-gptq"
 METRIC = "decode_tokens_per_s"
 UNIT = "tokens/s"
 
@@ -59,7 +66,8 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe).  Started well before
+    the timed region (nvidia-smi needs a second to enumerate an 8-GPU box); only samples between mark() and stop() count."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -68,11 +76,12 @@ class ClockSampler:
         self.lines = []
         self.proc = None
         self.index = index
+        self.first = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -81,13 +90,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, wait_s: float = 5.0):
+        """call right before the timed region: waits until nvidia-smi delivers, then forgets the earlier samples"""
+        if self.proc is None:
+            return
+        t_end = time.time() + wait_s
+        while not self.lines and time.time() < t_end:
+            time.sleep(0.02)
+        self.first = max(0, len(self.lines) - 1)
+
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -109,8 +127,7 @@ class ClockSampler:
 def cpu_reference_decode(arch: str, B: int, ctx: int, steps: int, warmup: int, sample_layers: int):
     """Times greedy decode steps of the reference's CPU path on a bounded sample: `sample_layers` of the model's layers
     (same widths, fp32, HF eager attention, padded rectangular KV at context `ctx`), scaled to the full depth.
-    Returns (tokens_per_s_full_model, cores, sample_description, ms_per_step_sample)."""
-    import torch
+    -> dict(value tokens/s of the full model, cores, sample, ms_per_step full depth, steps timed per sample)."""
     from oracle import causal_lm as ocl  # oracle/ is the checker + CPU baseline only (never on the product path)
     return ocl.time_decode(arch, B, ctx, steps, warmup, sample_layers)
 
@@ -121,15 +138,22 @@ def run_reference(args, workload):
     if rank != 0:
         return 0
     ctx = (L0 + L1) // 2
-    tps, cores, sample, ms = cpu_reference_decode(arch, B, ctx, args.steps, args.warmup, args.cpu_layers)
+    r = cpu_reference_decode(arch, B, ctx, args.steps, args.warmup, args.cpu_layers)
     line = {
-        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "arch": arch, "batch": B, "prompt_len": L0, "end_len": L1, "context": ctx},
-        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload, "arch": arch, "batch": B, "prompt_len": L0, "end_len": L1, "context": ctx,
+                   "steps_timed_per_sample": r["steps_timed"], "extrapolated_in_depth": r["extrapolated"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_extra and workload != "tiny-test":
+        try:  # BASELINE config[0]: gpt2 CausalLM fp32 CPU, bs=4, 128 -> 256 (whole model, really run; random-init: no weights here)
+            from oracle import causal_lm as ocl
+            line["extra"] = {"config0_gpt2_cpu": ocl.time_decode_gpt2(4, 192, steps=8, warmup=2)}
+        except Exception as e:  # noqa: BLE001
+            line["extra"] = {"config0_gpt2_cpu": {"failed": f"{type(e).__name__}: {e}"}}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -137,7 +161,7 @@ def run_reference(args, workload):
 # ======================================================================================================
 # GPU arm
 # ======================================================================================================
-def build_model(workload, world, rank, num_layers=None):
+def build_model(workload, world, rank, num_layers=None, cfg_override=None, weights=None, blocks=None):
     import torch
     import tgis_b200  # noqa: F401
     from tgis_b200.inference_engine import InferenceEngine
@@ -146,15 +170,17 @@ def build_model(workload, world, rank, num_layers=None):
     from tgis_b200.utils.synthetic import SyntheticWeights, llama_config, make_tokenizer
 
     arch, quantize, B, L0, L1 = WORKLOADS[workload]
-    cfg = llama_config(arch, quantize=quantize, max_position_embeddings=max(4096, L1 + 64), num_layers=num_layers)
+    cfg = cfg_override or llama_config(arch, quantize=quantize, max_position_embeddings=max(4096, L1 + 64), num_layers=num_layers)
     local = int(os.getenv("LOCAL_RANK", rank))
     torch.cuda.set_device(local % torch.cuda.device_count())
     device = torch.device("cuda", torch.cuda.current_device())
     pg = initialize_torch_distributed(world, rank)
-    weights = SyntheticWeights(cfg, device, torch.float16, pg, quantize=quantize)
+    if weights is None:
+        weights = SyntheticWeights(cfg, device, torch.float16, pg, quantize=quantize)
     tok = make_tokenizer(cfg.vocab_size)
     engine = InferenceEngine("<synthetic>", None, torch.float16, quantize, cfg, L1, weights=weights, tokenizer=tok)
-    blocks = B * ((L1 + 16) // 16 + 1) + 8
+    if blocks is None:
+        blocks = B * ((L1 + 16) // 16 + 1) + 8
     model = FlashCausalLM("<synthetic>", None, "tgis_native", torch.float16, quantize, cfg, engine=engine, num_kv_blocks=blocks)
     return model, cfg
 
@@ -170,7 +196,7 @@ def make_batch_pb(B, L0, n_new, batch_id=0):
 
 
 def algorithmic_bytes_per_step(cfg, quantize, B, ctx, tp):
-    """SURVEY.md §8d formula, per GPU."""
+    """SURVEY.md §8d formula, per GPU -> (whole step, attention KV read of one layer, linear weights incl. head)."""
     H, I, V, nl = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers
     d = H // cfg.num_attention_heads
     h, kv = cfg.num_attention_heads, cfg.num_key_value_heads
@@ -183,15 +209,14 @@ def algorithmic_bytes_per_step(cfg, quantize, B, ctx, tp):
     kv_read = B * ctx * nl * 2 * kv * d * 2
     kv_write = B * nl * 2 * kv * d * 2
     logits = B * V * 2
-    return (w_lin + w_head + kv_read + kv_write + logits) / tp, kv_read / tp / nl
+    return (w_lin + w_head + kv_read + kv_write + logits) / tp, kv_read / tp / nl, (w_lin + w_head) / tp
 
 
-def run_gpu(args, workload):
+def measure_workload(args, workload, world, rank, full: bool):
+    """One workload, the whole L0 -> L1 trajectory.  `full`: also the per-kernel rooflines (eager passes) and prefill detail."""
     import torch
     import torch.distributed as dist
 
-    world = int(os.getenv("WORLD_SIZE", "1"))
-    rank = int(os.getenv("RANK", "0"))
     arch, quantize, B, L0, L1 = WORKLOADS[workload]
     K, W = args.steps, args.warmup
     model, cfg = build_model(workload, world, rank, args.layers)
@@ -213,32 +238,55 @@ def run_gpu(args, workload):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
     # ---------------------------------------------------------------- prefill (timed once, reported beside the metric)
     batch, errs = model.batch_type.from_pb(make_batch_pb(B, L0, n_new), model.tokenizer, model.dtype, dev, None, None, True)
     assert not errs
+    e2e_ms, e2e_steps, e2e_ctx_sum = 0.0, 0, 0.0
+    host_ids = torch.empty(B, dtype=torch.int64).pin_memory()
     with torch.inference_mode():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        model.generate_token(batch, first=True)
+        toks = model.generate_token(batch, first=True)[0]
         e1.record()
         barrier()
         prefill_ms = max_over_ranks(e0.elapsed_time(e1))
-
-        # ------------------------------------------------------------ run the real trajectory up to the timed window
-        # phase A (device-resident "value"): window of K steps ending at context mid; phase B (e2e): K steps from mid.
-        start_a = mid - K - W
         cur = L0  # tokens cached before the next decode step (that step attends over cur + 1)
-        while cur < start_a:
-            model.generate_token(batch)
+
+        def e2e_segment(n_steps, toks, cur):
+            """n_steps decode steps through generate_token with host buffers in the timed region; -> (ms, toks, cur)"""
+            if n_steps <= 0:
+                return 0.0, toks, cur
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(n_steps):
+                host_ids.copy_(torch.tensor([t.token_id for t in toks], dtype=torch.int64))
+                batch.input_ids.copy_(host_ids, non_blocking=True)      # H2D: this step's input token ids
+                toks = model.generate_token(batch)[0]                    # D2H: the chosen ids (one read per step)
+            e1.record()
+            barrier()
+            wall = (time.perf_counter() - t0) * 1e3
+            return max_over_ranks(max(e0.elapsed_time(e1), wall)), toks, cur + n_steps
+
+        # ---- e2e, first half of the trajectory (3 untimed steps first: the fused state and its CUDA graph come to exist)
+        for _ in range(3):
+            toks = model.generate_token(batch)[0]
             cur += 1
-        # ---- phase A: device-resident loop through the fused step (no host round trip inside the timed region)
-        st_launch0 = None
-        for _ in range(3):  # make sure the fused state (and CUDA graph) of this batch exists
-            model.generate_token(batch)
-            cur += 1
+        n_eager = K if full else 0
+        start_a = mid - (K + n_eager) // 2 - W
+        seg_steps = max(0, start_a - cur)
+        ctx0 = cur
+        ms, toks, cur = e2e_segment(seg_steps, toks, cur)
+        e2e_ms += ms
+        e2e_steps += seg_steps
+        e2e_ctx_sum += seg_steps * (ctx0 + (seg_steps + 1) / 2.0)
+
+        # ---- device-resident window around the mean context: no host round trip inside the timed region
         st = batch._fused
-        kv = batch.past_key_values
+        batch.input_ids.copy_(torch.tensor([t.token_id for t in toks], dtype=torch.int64))
 
         def device_step(use_graph=True):
             model._run_fused_step(batch, st, use_graph)
@@ -248,26 +296,35 @@ def run_gpu(args, workload):
         for _ in range(W):
             device_step()
             cur += 1
-        timing = lib.b200_timing_create(K * cfg.num_hidden_layers + 8)
-        # eager steps carry the per-kernel events; graph replays cannot (events are not captured), so the roofline
-        # pass runs the same K steps eagerly first, then the headline pass replays the graph
-        lib.b200_timing_attach(timing, 1)
-        barrier()
-        for _ in range(K):
-            device_step(use_graph=False)
-        barrier()
-        lib.b200_timing_attach(None, 0)
-        tot = ctypes.c_float(0)
-        n_timed = lib.b200_timing_collect(timing, ctypes.byref(tot))
-        if n_timed < 0:
-            raise RuntimeError(lib.b200_last_error().decode())
-        attn_ms = tot.value / max(n_timed, 1)
-        ctx_roof = cur + (K + 1) / 2.0  # mean context (incl. the token written) over those K steps
-        cur += K
+        attn_ms = gemm_ms = None
+        n_attn = n_gemm = 0
+        ctx_roof = None
+        if full:
+            # eager steps carry the per-kernel events (events are not captured into graphs); two kernel families, K/2 steps each
+            which_gemm = 2 if quantize == "gptq" else 3  # B200_TIME_GEMM_W4A16 / B200_TIME_GEMM_F16
+            halves = [(1, K - K // 2), (which_gemm, K // 2)]
+            for which, n_steps in halves:
+                timing = lib.b200_timing_create(n_steps * (4 * cfg.num_hidden_layers + 2) + 8)
+                lib.b200_timing_attach(timing, which)
+                barrier()
+                for _ in range(n_steps):
+                    device_step(use_graph=False)
+                barrier()
+                lib.b200_timing_attach(None, 0)
+                tot = ctypes.c_float(0)
+                n_timed = lib.b200_timing_collect(timing, ctypes.byref(tot))
+                if n_timed < 0:
+                    raise RuntimeError(lib.b200_last_error().decode())
+                lib.b200_timing_destroy(timing)
+                if which == 1:
+                    attn_ms, n_attn = tot.value / max(n_timed, 1), n_timed
+                    ctx_roof = cur + (n_steps + 1) / 2.0
+                else:
+                    gemm_ms, n_gemm = tot.value / max(n_steps, 1), n_timed  # per step
+                cur += n_steps
         # headline pass
-        sampler = ClockSampler(torch.cuda.current_device())
-        sampler.start()
         launches0 = lib.b200_launch_count()
+        sampler.mark()
         barrier()
         e0.record()
         for _ in range(K):
@@ -278,90 +335,200 @@ def run_gpu(args, workload):
         clocks = sampler.stop()
         ctx_value = cur + (K + 1) / 2.0
         cur += K
-        launches_eager_equiv = None
-        # the host mirrors of the lengths advance too (generate_token was bypassed for 2K+W steps)
+        # the host mirrors of the lengths advance too (generate_token was bypassed for these steps)
+        skipped = W + n_eager + K
         for i in range(B):
-            batch.input_lengths[i] += 2 * K + W
-        batch.max_seqlen += 2 * K + W
-        batch.cu_seqlens.add_(batch.cu_seqlens_q * (2 * K + W))
-        for i in range(B):
-            batch.next_token_chooser.current_tokens[i] += 2 * K + W
-
-        # ---- phase B: end to end through generate_token with host buffers
-        host_ids = torch.empty(B, dtype=torch.int64).pin_memory()
-        toks = model.generate_token(batch)[0]
-        cur += 1
-        for _ in range(W):
-            toks = model.generate_token(batch)[0]
-            cur += 1
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(K):
-            host_ids.copy_(torch.tensor([t.token_id for t in toks], dtype=torch.int64))
-            batch.input_ids.copy_(host_ids, non_blocking=True)      # H2D: this step's input token ids
-            toks = model.generate_token(batch)[0]                    # D2H: the chosen ids (one read per step)
-        e1.record()
-        barrier()
-        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), e2e_wall_ms))
-        ctx_e2e = cur + (K + 1) / 2.0
-        cur += K
-
-    # graph replays launch the same kernels as an eager step; count them from one eager step's counter delta
-    l0 = lib.b200_launch_count()
-    with torch.inference_mode():
+            batch.input_lengths[i] += skipped
+            batch.next_token_chooser.current_tokens[i] += skipped
+        batch.max_seqlen += skipped
+        batch.cu_seqlens.add_(batch.cu_seqlens_q * skipped)
+        # graph replays launch the same kernels as an eager step; count them from one eager step's counter delta
+        l0 = lib.b200_launch_count()
         device_step(use_graph=False)
         torch.cuda.synchronize()
-    launches_per_step = lib.b200_launch_count() - l0
+        launches_per_step = lib.b200_launch_count() - l0
+        cur += 1
+        for i in range(B):
+            batch.input_lengths[i] += 1
+            batch.next_token_chooser.current_tokens[i] += 1
+        batch.max_seqlen += 1
+        batch.cu_seqlens.add_(batch.cu_seqlens_q)
+
+        # ---- e2e, second half of the trajectory: up to the last token the requests asked for
+        toks = model.generate_token(batch)[0]
+        cur += 1
+        seg_steps = max(0, (L1 - 1) - cur)
+        ctx0 = cur
+        ms, toks, cur = e2e_segment(seg_steps, toks, cur)
+        e2e_ms += ms
+        e2e_steps += seg_steps
+        e2e_ctx_sum += seg_steps * (ctx0 + (seg_steps + 1) / 2.0)
 
     hbm_peak, peak_kind = peaks()
-    step_bytes, attn_bytes = algorithmic_bytes_per_step(cfg, quantize, B, ctx_value, world)
-    _, attn_bytes_roof = algorithmic_bytes_per_step(cfg, quantize, B, ctx_roof, world)
+    step_bytes, _, w_bytes = algorithmic_bytes_per_step(cfg, quantize, B, ctx_value, world)
     value = B * K / (dev_ms / 1e3)
-    e2e_value = B * K / (e2e_ms / 1e3)
-    achieved = attn_bytes_roof / (attn_ms / 1e3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            with open(tpath) as f:
-                traffic = json.load(f).get(workload, {}).get("attn_decode_traffic_bytes_per_launch")
-        except Exception:
-            traffic = None
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16" if quantize is None else "int4 weights x f16 activations, f32 accumulate", "data": "synthetic",
-        "config": {"workload": workload, "arch": arch, "quantize": quantize, "batch": B, "prompt_len": L0, "end_len": L1,
-                   "mean_context_timed": ctx_value, "kv_block": 16, "parallelism": f"tp{world}",
-                   "l2_policy": "inputs larger than L2 (KV + weights per step >> 126 MB)",
-                   "layers": cfg.num_hidden_layers},
-        "tokens_per_s_per_gpu": value / world,
+    res = {
+        "workload": workload, "value": value, "ms_per_step": dev_ms / K, "mean_context_timed": ctx_value,
         "step_roofline": {"algorithmic_bytes_per_step_per_gpu": step_bytes, "hbm_gbs_achieved": step_bytes / (dev_ms / K / 1e3) / 1e9,
                           "frac_of_hbm_peak": step_bytes / (dev_ms / K / 1e3) / 1e9 / hbm_peak, "peak_kind": peak_kind},
         "prefill": {"tokens": B * L0, "ms": prefill_ms, "tokens_per_s": B * L0 / (prefill_ms / 1e3)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 8,
-                "ms_per_step": e2e_ms / K, "mean_context": ctx_e2e, "api": "FlashCausalLM.generate_token"},
-        "gpu_launches": int(launches_per_step * K),
-        "clocks": clocks,
-        "roofline": {"kernel": "attn_decode_paged_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
-                     "algorithmic_bytes_per_launch": attn_bytes_roof, "avg_launch_ms": attn_ms, "launches_timed": n_timed,
-                     "share_of_step": attn_ms * cfg.num_hidden_layers / (dev_ms / K)},
+        "e2e": {"value": B * e2e_steps / (e2e_ms / 1e3) if e2e_ms > 0 else None, "unit": UNIT, "h2d_bytes_per_step": B * 8,
+                "d2h_bytes_per_step": B * 8, "ms_per_step": e2e_ms / max(e2e_steps, 1), "steps": e2e_steps,
+                "mean_context": e2e_ctx_sum / max(e2e_steps, 1), "api": "FlashCausalLM.generate_token",
+                "trajectory": f"every decode step {L0}->{L1} outside the {skipped + 5}-step device-timed window"},
+        "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step), "clocks": clocks,
+        "arch": arch, "quantize": quantize, "batch": B, "prompt_len": L0, "end_len": L1, "layers": cfg.num_hidden_layers,
     }
+    if full and attn_ms:
+        _, attn_bytes_roof, _ = algorithmic_bytes_per_step(cfg, quantize, B, ctx_roof, world)
+        achieved = attn_bytes_roof / (attn_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(workload, {}).get("attn_decode_traffic_bytes_per_launch")
+            except Exception:
+                traffic = None
+        res["roofline"] = {"kernel": "attn_decode_paged_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                           "algorithmic_bytes_per_launch": attn_bytes_roof, "avg_launch_ms": attn_ms, "launches_timed": n_attn,
+                           "share_of_step": attn_ms * cfg.num_hidden_layers / (dev_ms / K),
+                           "timing": "CUDA events around each eager launch (adds the event gaps: graph-replayed launches are shorter, "
+                                     "see profiles/ step traces)"}
+        if gemm_ms:
+            res["roofline"]["gemm"] = {"kernel": "gemm_w4a16_kernel" if quantize == "gptq" else "gemm_f16_kernel", "bound": "hbm",
+                                       "algorithmic_weight_bytes_per_step": w_bytes, "ms_per_step": gemm_ms,
+                                       "achieved": w_bytes / (gemm_ms / 1e3) / 1e9, "unit": "GB/s",
+                                       "frac": w_bytes / (gemm_ms / 1e3) / 1e9 / hbm_peak, "share_of_step": gemm_ms / (dev_ms / K),
+                                       "launches_timed": n_gemm}
+    # free everything before the next workload
+    del batch, st, model
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def self_check(arch: str, quantize):
+    """2 layers of the workload's widths (small vocabulary), ragged prompts, greedy decode through from_pb / generate_token
+    (prefill, eager steps, the CUDA-graph-replayed fused step) vs the CPU oracle; exact outside the 2-ulp tie band."""
+    import tempfile
+
+    import torch
+    from safetensors.torch import save_file
+
+    from oracle import llama as oll  # checker only
+    from tgis_b200 import pb
+    from tgis_b200.inference_engine import InferenceEngine
+    from tgis_b200.models.flash_causal_lm import FlashCausalLM
+    from tgis_b200.utils.dist import FakeGroup
+    from tgis_b200.utils.synthetic import ARCHS, llama_config, make_tokenizer
+    from tgis_b200.utils.weights import Weights
+
+    H, I, _, h, kv, _ = ARCHS[arch]
+    cfg = llama_config(arch, quantize=quantize, max_position_embeddings=512, num_layers=2)
+    cfg.vocab_size = 4096
+    ocfg = oll.LlamaConfig(H, I, 2, h, kv, cfg.vocab_size, cfg.rms_norm_eps, cfg.rope_theta)
+    sd = oll.make_state_dict(ocfg, seed=11, quantize=quantize, std=0.02)
+    dev = "cuda:0"
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "model.safetensors")
+        save_file({k: v.contiguous() for k, v in sd.items()}, path)
+        weights = Weights([path], device=dev, dtype=torch.float16, process_group=FakeGroup(0, 1))
+        tok = make_tokenizer(cfg.vocab_size)
+        engine = InferenceEngine(tmp, None, torch.float16, quantize, cfg, 512, weights=weights, tokenizer=tok)
+        model = FlashCausalLM(tmp, None, "tgis_native", torch.float16, quantize, cfg, engine=engine, num_kv_blocks=128)
+    g = torch.Generator().manual_seed(0)
+    lens = (40, 64, 17, 33, 48, 5, 64, 21)
+    prompts = [torch.randint(4, cfg.vocab_size, (L,), generator=g).tolist() for L in lens]
+    n_new = 8
+    reqs = [pb.Request(id=i, inputs=" ".join(f"<tok{t}>" for t in p), input_length=len(p), max_output_length=n_new,
+                       parameters=pb.NextTokenChooserParameters(temperature=0.0, top_p=1.0, min_new_tokens=n_new))
+            for i, p in enumerate(prompts)]
+    got = [[] for _ in prompts]
+    with torch.inference_mode():
+        batch, errs = model.batch_type.from_pb(pb.Batch(id=0, requests=reqs), tok, torch.float16, model.device, None, None, True)
+        assert not errs
+        out = model.generate_token(batch, first=True)
+        for _ in range(n_new - 1):
+            for t in out[0]:
+                got[t.request_id].append(t.token_id)
+            out = model.generate_token(batch)
+        for t in out[0]:
+            got[t.request_id].append(t.token_id)
+    torch.cuda.synchronize()
+    oracle = oll.LlamaOracle(oll.build_shards(ocfg, sd, 1))
+    ref, ref_logits = oracle.generate_greedy(prompts, n_new, banned_token=cfg.eos_token_id)
+    checked = mismatches = ties = 0
+    for b in range(len(prompts)):
+        for step in range(n_new):
+            lg = ref_logits[step][b].float().clone()
+            lg[cfg.eos_token_id] = float("-inf")
+            top2 = lg.topk(2).values
+            if float(top2[0] - top2[1]) <= 2 * max(abs(float(top2[0])), 1.0) * 2.0 ** -10:
+                ties += 1
+                break  # after a tie the continuations may legitimately differ
+            checked += 1
+            if got[b][step] != int(ref[b, step]):
+                mismatches += 1
+                break
+    del model, batch
+    gc.collect()
+    torch.cuda.empty_cache()
+    return {"model": f"{arch} widths, 2 layers, vocab 4096, {quantize or 'fp16'}", "sequences": len(prompts), "new_tokens": n_new,
+            "tokens_checked": checked, "ties_skipped": ties, "mismatches_outside_tie_band": mismatches,
+            "steps_through_cuda_graph": max(0, n_new - 1 - 2)}
+
+
+def run_gpu(args, workload):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.getenv("WORLD_SIZE", "1"))
+    rank = int(os.getenv("RANK", "0"))
+    main = measure_workload(args, workload, world, rank, full=True)
+    arch, quantize, B, L0, L1 = WORKLOADS[workload]
+    line = {
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16" if quantize is None else "int4 weights x f16 activations, f32 accumulate", "data": "synthetic",
+        "config": {"workload": workload, "arch": arch, "quantize": quantize, "batch": B, "prompt_len": L0, "end_len": L1,
+                   "mean_context_timed": main["mean_context_timed"], "kv_block": 16, "parallelism": f"tp{world}",
+                   "l2_policy": "inputs larger than L2 (KV + weights per step >> 126 MB)", "layers": main["layers"]},
+        "tokens_per_s_per_gpu": main["value"] / world,
+        "step_roofline": main["step_roofline"], "prefill": main["prefill"], "e2e": main["e2e"],
+        "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
+    }
+    if "roofline" in main:
+        line["roofline"] = main["roofline"]
+    extra = {}
+    if not args.no_extra and args.workload is None:
+        other = "llama2-7b-gptq" if world == 1 else "llama2-7b-fp16"  # BASELINE config[2] / config[3]
+        try:
+            r = measure_workload(args, other, world, rank, full=False)
+            extra[other] = {k: r[k] for k in ("value", "ms_per_step", "mean_context_timed", "step_roofline", "prefill", "e2e", "clocks",
+                                              "launches_per_step", "arch", "quantize", "batch", "prompt_len", "end_len")}
+            extra[other]["parallelism"] = f"tp{world}"
+        except Exception as e:  # noqa: BLE001
+            extra[other] = {"failed": f"{type(e).__name__}: {e}"}
     if rank == 0:
+        if world == 1 and not args.no_extra:
+            try:
+                line["self_check"] = self_check(arch, quantize)
+            except Exception as e:  # noqa: BLE001
+                line["self_check"] = {"failed": f"{type(e).__name__}: {e}"}
         if not args.no_cpu_baseline and world == 1:
             try:
-                tps, cores, sample, ms = cpu_reference_decode(arch, B, mid, max(2, min(4, K)), 1, args.cpu_layers)
-                line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+                r = cpu_reference_decode(arch, B, (L0 + L1) // 2, max(2, min(4, args.steps)), 1, args.cpu_layers)
+                line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {type(e).__name__}: {e}"}
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
-        # NCCL kernels live inside the captured CUDA graphs: tearing the communicator down while they exist can hang, so
+        # collectives live inside the captured CUDA graphs: tearing the communicator down while they exist can hang, so
         # rendezvous on the host-side store instead of an NCCL barrier, then leave without destroy_process_group()
         torch.cuda.synchronize()
         sys.stdout.flush()
@@ -388,11 +555,11 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="debug: override the number of layers")
     ap.add_argument("--cpu-layers", type=int, default=2, help="layers in the CPU baseline's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the second workload, the self-check and the gpt2 CPU line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    world = int(os.getenv("WORLD_SIZE", "1"))
-    workload = args.workload or ("llama2-7b-gptq" if max(args.gpus, world) == 1 else "llama2-7b-fp16")
+    workload = args.workload or DEFAULT_WORKLOAD
     if args.impl == "reference":
         return run_reference(args, workload)
     return run_gpu(args, workload)

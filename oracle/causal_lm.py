@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import os
 import time
-from typing import Tuple
 
 import torch
 
@@ -70,9 +69,10 @@ def _time_steps(model, cfg, B: int, ctx: int, steps: int, warmup: int) -> float:
     return times[len(times) // 2]
 
 
-def time_decode(arch: str, B: int, ctx: int, steps: int, warmup: int, sample_layers: int = 2,
-                max_cpu_steps: int = 6) -> Tuple[float, int, str, float]:
-    """-> (tokens/s extrapolated to the full model, threads used, sample description, ms per step of the larger sample)."""
+def time_decode(arch: str, B: int, ctx: int, steps: int, warmup: int, sample_layers: int = 2, max_cpu_steps: int = 6) -> dict:
+    """-> {"value": tokens/s extrapolated to the full model, "cores": threads used, "sample": description,
+           "ms_per_step": extrapolated full-depth milliseconds per step (value == B / that), "steps_timed": steps really timed per
+           sample, "extrapolated": True}.  A 32-layer fp32 step at B = 64 takes ~6 s on 16 cores, so the sample is bounded."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n_full = ARCHS[arch][2]
@@ -89,5 +89,40 @@ def time_decode(arch: str, B: int, ctx: int, steps: int, warmup: int, sample_lay
     t_full = t1 + (n_full - 1) * t_layer
     sample = (f"HF LlamaForCausalLM fp32 eager CPU decode step, B={B}, context={ctx}, full width; timed 1 and "
               f"{1 + sample_layers} of {n_full} layers ({steps} steps each, median) and extrapolated linearly in depth "
-              f"(t1={t1 * 1e3:.1f} ms, per-layer={t_layer * 1e3:.1f} ms)")
-    return B / t_full, cores, sample, t2 * 1e3
+              f"(t1={t1 * 1e3:.1f} ms, per-layer={t_layer * 1e3:.1f} ms, full depth={t_full * 1e3:.1f} ms per step)")
+    return {"value": B / t_full, "cores": cores, "sample": sample, "ms_per_step": t_full * 1e3, "steps_timed": steps,
+            "extrapolated": True}
+
+
+def time_decode_gpt2(B: int = 4, ctx: int = 192, steps: int = 8, warmup: int = 2) -> dict:
+    """BASELINE config[0]: the reference's CPU CausalLM path on gpt2 (124M: 12 layers, 768 wide, 12 heads, vocab 50257), fp32,
+    bs = 4, sequence 128 -> 256 (mid context 192), greedy - integration_tests/test_cases_gpt2.yaml runs this model through the
+    same path.  The whole model is run (no extrapolation); weights are random-init (no checkpoint in the image), which does not
+    change the arithmetic per step."""
+    from transformers import DynamicCache, GPT2Config, GPT2LMHeadModel
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    cfg = GPT2Config()
+    model = GPT2LMHeadModel(cfg).to(torch.float32).eval()
+    g = torch.Generator().manual_seed(0)
+    prompt = torch.randint(0, cfg.vocab_size, (B, ctx - 1), generator=g)
+    times = []
+    with torch.inference_mode():
+        out = model(input_ids=prompt, use_cache=True)  # prefill builds the KV cache the decode steps grow
+        cache = out.past_key_values
+        ids = out.logits[:, -1, :].argmax(-1, keepdim=True)
+        for i in range(warmup + steps):
+            L = ctx - 1 + i
+            attn = torch.ones(B, L + 1, dtype=torch.long)
+            t0 = time.perf_counter()
+            out = model(input_ids=ids, attention_mask=attn, past_key_values=cache, use_cache=True)
+            dt = time.perf_counter() - t0
+            ids = out.logits[:, -1, :].argmax(-1, keepdim=True)
+            cache = out.past_key_values
+            if i >= warmup:
+                times.append(dt)
+    times.sort()
+    t = times[len(times) // 2]
+    return {"workload": "gpt2 CausalLM fp32 CPU, bs=4, seq 128->256 (BASELINE config[0])", "value": B / t, "unit": "tokens/s",
+            "ms_per_step": t * 1e3, "steps_timed": steps, "cores": cores, "extrapolated": False, "weights": "random-init"}

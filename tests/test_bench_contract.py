@@ -23,6 +23,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "decode_tokens_per_s" and d["unit"] == "tokens/s"
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] >= 3 and d["value"] > 0
     assert d["config"]["workload"] == "tiny-test"
+    # the line is self-consistent: value == batch / extrapolated full-depth step time, and it says how many steps really ran
+    assert abs(d["value"] - d["config"]["batch"] / (d["ms_per_step"] / 1e3)) <= 1e-6 * d["value"]
+    assert d["config"]["steps_timed_per_sample"] >= 1 and d["config"]["extrapolated_in_depth"] is True
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

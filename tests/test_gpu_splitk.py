@@ -102,7 +102,8 @@ def test_rmsnorm_consumes_partials_bit_exactly(ops, quant, T, H, K):
     n_ref, r_ref = ops.rmsnorm_residual(h, res, gamma, 1e-5)
     n_got, r_got = ops.rmsnorm_residual_splitk(parts, res, gamma, 1e-5)
     torch.cuda.synchronize()
-    assert torch.equal(r_got, r_ref) and torch.equal(n_got, n_ref)
+    assert torch.equal(r_got, r_ref), f"residual_out differs: {(r_got != r_ref).sum().item()} elements"
+    assert torch.equal(n_got, n_ref), f"normed differs: {(n_got != n_ref).sum().item()} elements"
 
 
 @pytest.mark.parametrize("h,kv,d", [(32, 32, 128), (32, 8, 128), (4, 1, 128), (32, 4, 64)])

@@ -464,9 +464,11 @@ extern "C" int b200_rmsnorm_residual(const void* h, const void* residual, const 
   }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)H * sizeof(float);
-  constexpr auto kernel = rmsnorm_residual_kernel<256, false>;
+  // 512 threads like the split-K and the fused all-reduce variants: the same thread -> element mapping and reduction tree, so the
+  // three produce bit-identical statistics for the same row
+  constexpr auto kernel = rmsnorm_residual_kernel<512, false>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  B200_LAUNCH_AS("rmsnorm_residual_kernel", kernel, dim3((unsigned)T), dim3(256), smem, st, (const __half*)h, (const __half*)residual,
+  B200_LAUNCH_AS("rmsnorm_residual_kernel", kernel, dim3((unsigned)T), dim3(512), smem, st, (const __half*)h, (const __half*)residual,
                  (const __half*)gamma, (__half*)normed_out, (__half*)residual_out, (int)H, eps, B200SplitK{});
   b200_count_launches(1);
   return B200_OK;

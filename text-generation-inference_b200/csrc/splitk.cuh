@@ -36,14 +36,14 @@ __device__ __forceinline__ SplitKRef splitk_ref(const B200SplitK& d, int t, int 
 __device__ __forceinline__ float4 splitk_sum4(const B200SplitK& d, int t, int n) {
   const SplitKRef ref = splitk_ref(d, t, n);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int c0 = 0; c0 < ref.n_contrib; c0 += 4) {  // loads batched by 4, summed in contributor order
-    float4 ld[4];
+  for (int c0 = 0; c0 < ref.n_contrib; c0 += 8) {  // 8 loads in flight (L2 latency bound), summed in contributor order
+    float4 ld[8];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc)
+    for (int cc = 0; cc < 8; ++cc)
       ld[cc] = c0 + cc < ref.n_contrib ? __ldcg(reinterpret_cast<const float4*>(ref.base + (size_t)(c0 + cc) * ref.stride))
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < 8; ++cc) {
       if (c0 + cc < ref.n_contrib) { acc.x += ld[cc].x; acc.y += ld[cc].y; acc.z += ld[cc].z; acc.w += ld[cc].w; }
     }
   }
@@ -57,12 +57,12 @@ __device__ __forceinline__ float4 splitk_sum4(const B200SplitK& d, int t, int n)
 __device__ __forceinline__ float splitk_sum1(const B200SplitK& d, int t, int n) {
   const SplitKRef ref = splitk_ref(d, t, n);
   float acc = 0.f;
-  for (int c0 = 0; c0 < ref.n_contrib; c0 += 4) {
-    float ld[4];
+  for (int c0 = 0; c0 < ref.n_contrib; c0 += 8) {
+    float ld[8];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) ld[cc] = c0 + cc < ref.n_contrib ? __ldcg(ref.base + (size_t)(c0 + cc) * ref.stride) : 0.f;
+    for (int cc = 0; cc < 8; ++cc) ld[cc] = c0 + cc < ref.n_contrib ? __ldcg(ref.base + (size_t)(c0 + cc) * ref.stride) : 0.f;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc)
+    for (int cc = 0; cc < 8; ++cc)
       if (c0 + cc < ref.n_contrib) acc += ld[cc];
   }
   if (d.bias) acc += __half2float(reinterpret_cast<const __half*>(d.bias)[n]);
