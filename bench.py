@@ -11,6 +11,9 @@ Workloads (BASELINE.json):
                    Measured in the same run at N=1 and reported under "extra".
   llama2-7b-fp16   config[3]: Llama-2-7B fp16, tensor parallel, bs=64.  Measured in the same run at N>1, under "extra".
   tinyllama-fp16   config[1]: TinyLlama-1.1B fp16, bs=32, 512->1024 (on request).
+  llama3-70b-gptq-mixed   config[4]: Llama-3-70B int4, NUM_SHARD=8, continuous batching (Poisson arrivals, prompts U[256,1024], outputs
+                   U[128,512], up to 128 running) through Prefill / NextToken with prune + concatenate; llama3-8b-gptq-mixed is the
+                   same session on one GPU (on request).
 
 A "step" is one decode step of the whole batch (one token per sequence).  The run really generates the whole trajectory
 L0 -> L1 from the prompt, so KV contents, block tables and lengths are what the serving path produces:
@@ -50,6 +53,13 @@ WORKLOADS = {
     "llama2-7b-fp16": ("llama-2-7b", None, 64, 1024, 2048),
     "tinyllama-fp16": ("tinyllama-1.1b", None, 32, 512, 1024),
     "tiny-test": ("tiny-test", None, 4, 32, 256),
+}
+# continuous-batching sessions (BASELINE config[4] and a single-GPU sibling): (arch, quantize, max batch, prompt range, output range,
+# requests, Poisson arrivals per second)
+MIXED_WORKLOADS = {
+    "llama3-70b-gptq-mixed": ("llama-3-70b", "gptq", 128, (256, 1024), (128, 512), 384, 60.0),
+    "llama3-8b-gptq-mixed": ("llama-3-8b", "gptq", 128, (256, 1024), (128, 512), 384, 120.0),
+    "tiny-test-mixed": ("tiny-test", None, 8, (8, 60), (4, 24), 40, 2000.0),
 }
 DEFAULT_WORKLOAD = "llama3-8b-gptq"
 METRIC = "decode_tokens_per_s"
@@ -409,6 +419,104 @@ def measure_workload(args, workload, world, rank, full: bool):
     return res
 
 
+def run_mixed(args, workload):
+    """BASELINE config[4]: continuous batching with add-on prefills, driven through the shard's own Prefill / NextToken messages
+    by tools/router_sim.py (the Rust router's loop restated).  Decode-step and prefill throughput are reported separately."""
+    import torch
+    import torch.distributed as dist
+
+    from tools import router_sim
+
+    world = int(os.getenv("WORLD_SIZE", "1"))
+    rank = int(os.getenv("RANK", "0"))
+    arch, quantize, max_bs, prompt_range, new_range, n_req, rate = MIXED_WORKLOADS[workload]
+    n_req = args.requests or n_req
+    max_len = prompt_range[1] + new_range[1]
+    WORKLOADS[workload] = (arch, quantize, max_bs, prompt_range[1], max_len)
+    blocks = max_bs * ((max_len + 16) // 16 + 1) + 8
+    model, cfg = build_model(workload, world, rank, args.layers, blocks=blocks)
+    from tgis_b200 import _lib, pb
+    from tgis_b200.server import Cache, TextGenerationService
+    lib = _lib.load()
+    service = TextGenerationService(model, Cache(), ["unix:///dev/null"])
+    requests = router_sim.make_requests(n_req, rate, prompt_range, new_range, cfg.vocab_size, seed=0, filler=3)  # "test " * L
+    budget = max_bs * max_len
+    bytes_acc = {"decode": 0.0}
+    H, I, V, nl = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers
+    d = H // cfg.num_attention_heads
+
+    def on_step(bs, ctx_sum):
+        step_bytes, _, _ = algorithmic_bytes_per_step(cfg, quantize, 1, 0, world)        # weights + head (+ 1 row of logits)
+        kv = (ctx_sum + bs) * nl * 2 * cfg.num_key_value_heads * d * 2 / world              # KV read of every context (+ the new token)
+        bytes_acc["decode"] += step_bytes + kv + (bs - 1) * V * 2 / world
+
+    def sync():
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    l0 = lib.b200_launch_count()
+    if world > 1:
+        dist.barrier()
+    sampler.mark()
+    with torch.inference_mode():
+        out = router_sim.run_session(service, pb, requests, max_bs, lambda p: "test " * len(p), max_batch_tokens=budget, sync=sync,
+                                     on_decode_step=on_step)
+    clocks = sampler.stop()
+    st = out["stats"]
+    launches = lib.b200_launch_count() - l0
+    hbm_peak, peak_kind = peaks()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=model.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    decode_s, prefill_s = maxr(st["decode_s"]), maxr(st["prefill_s"])
+    value = st["decode_tokens"] / decode_s
+    assert all(len(out["tokens"][r.id]) == r.max_new for r in requests), "a request did not receive all its tokens"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": st["decode_steps"], "warmup": 0,
+        "ms_per_step": decode_s / max(st["decode_steps"], 1) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16" if quantize is None else "int4 weights x f16 activations, f32 accumulate", "data": "synthetic",
+        "config": {"workload": workload, "arch": arch, "quantize": quantize, "max_batch": max_bs, "prompt_len": list(prompt_range),
+                   "new_tokens": list(new_range), "requests": n_req, "poisson_arrivals_per_s": rate, "seed": 0, "kv_block": 16,
+                   "parallelism": f"tp{world}", "layers": cfg.num_hidden_layers,
+                   "driver": "tools/router_sim.py: add-on Prefill (to_prune) + NextToken over every cached batch id, as router/src/batcher.rs",
+                   "timing": "wall clock around each RPC, device synchronised on both sides (host bookkeeping of prune / concatenate included)"},
+        "tokens_per_s_per_gpu": value / world,
+        "decode": {"tokens": st["decode_tokens"], "seconds": decode_s, "steps": st["decode_steps"],
+                   "mean_batch": st["batch_size_sum"] / max(st["decode_steps"], 1), "max_batch": st["max_batch"],
+                   "steps_after_a_concatenate": st["concat_steps"]},
+        "prefill": {"tokens": st["prefill_tokens"], "ms": prefill_s * 1e3, "calls": st["prefill_calls"],
+                    "tokens_per_s": st["prefill_tokens"] / prefill_s if prefill_s > 0 else None},
+        "step_roofline": {"algorithmic_bytes_per_gpu_all_decode_steps": bytes_acc["decode"],
+                          "hbm_gbs_achieved": bytes_acc["decode"] / decode_s / 1e9,
+                          "frac_of_hbm_peak": bytes_acc["decode"] / decode_s / 1e9 / hbm_peak, "peak_kind": peak_kind},
+        "e2e": {"value": (st["decode_tokens"] + st["prefill_calls"]) / (decode_s + prefill_s), "unit": UNIT,
+                "note": "generated tokens / (prefill + decode time): the session as the router sees it, host buffers in and out of every RPC",
+                "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            store.add("bench_done", 1)
+            t_end = time.time() + 30
+            while int(store.add("bench_done", 0)) < world and time.time() < t_end:
+                time.sleep(0.05)
+        except Exception:
+            time.sleep(1.0)
+        os._exit(0)
+    return 0
+
+
 def self_check(arch: str, quantize):
     """2 layers of the workload's widths (small vocabulary), ragged prompts, greedy decode through from_pb / generate_token
     (prefill, eager steps, the CUDA-graph-replayed fused step) vs the CPU oracle; exact outside the 2-ulp tie band."""
@@ -551,7 +659,8 @@ def main():
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS) + list(MIXED_WORKLOADS))
+    ap.add_argument("--requests", type=int, default=None, help="mixed workloads: number of requests in the session")
     ap.add_argument("--layers", type=int, default=None, help="debug: override the number of layers")
     ap.add_argument("--cpu-layers", type=int, default=2, help="layers in the CPU baseline's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -560,6 +669,12 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     workload = args.workload or DEFAULT_WORKLOAD
+    if workload in MIXED_WORKLOADS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the continuous-batching session is a GPU-arm workload; the CPU arm times "
+                                                                  "single decode steps (use a decode workload)"}))
+            return 0
+        return run_mixed(args, workload)
     if args.impl == "reference":
         return run_reference(args, workload)
     return run_gpu(args, workload)

@@ -124,6 +124,19 @@ int b200_attn_prefill_varlen(const void* q, int64_t q_token_stride, const void* 
                              int64_t v_token_stride, const int32_t* cu_seqlens, void* out, int64_t out_token_stride, int B,
                              int max_s, int n_heads, int n_kv_heads, int head_dim, float softmax_scale, int causal, void* stream);
 
+/* ---- prefill / chunked-prefill attention over the paged pool (tcgen05 + TMA) ----------------------------
+ * Same reference op as b200_attn_prefill_varlen, but K and V come from the block pool, which the step's own tokens have
+ * already been appended to (b200_rope_kv_write_paged): the queries of a sequence may follow a cached context
+ * (paged_llama_modeling.py:253-264 attends a prefill over the fresh K/V only; an add-on prefill after a prompt prefix, a chunked
+ * prefill or a mixed prefill + decode step need this form).  Sequence b owns query tokens cu_seqlens_q[b] .. cu_seqlens_q[b+1]
+ * of q (T_q tokens, head-major [n_heads][d] at q + t * q_token_stride); context_lens[b] counts its tokens in the pool including
+ * them; query i sits at absolute position context_lens[b] - n_q(b) + i and attends keys 0 .. that position.  num_blocks = blocks
+ * of the pool (its first dimension); max_q = the largest n_q. */
+int b200_attn_prefill_paged(const void* q, int64_t q_token_stride, int64_t T_q, const void* k_pool, const void* v_pool,
+                            int64_t num_blocks, const int32_t* block_table, int64_t block_table_stride, const int32_t* context_lens,
+                            const int32_t* cu_seqlens_q, void* out, int64_t out_token_stride, int B, int max_q, int n_heads,
+                            int n_kv_heads, int head_dim, float softmax_scale, void* stream);
+
 /* ---- linears ------------------------------------------------------------------------------------------
  * workspace: >= b200_gemm_workspace_bytes(T, N, K) bytes; its first 64 KiB must have been zeroed once (split-K tile
  * counters; the kernels re-arm them).  NULL disables split-K. */
@@ -309,6 +322,11 @@ typedef struct {
   void* p2p_norm;   /* tensor parallel: b200_p2p_create window for b200_p2p_allreduce_rmsnorm (the layer boundary runs inside the
                        step, no host-side collective), or NULL: the caller all-reduces `hidden` between the block calls */
   void* p2p_argmax; /* tensor parallel: window for b200_p2p_argmax (sharded head -> next_ids), or NULL */
+  /* prefill steps: */
+  int64_t kv_num_blocks; /* blocks of the pool: > 0 lets a prefill step attend through the pool (b200_attn_prefill_paged; needs
+                            block_table + context_lens, context_lens counting the step's tokens), 0 = b200_attn_prefill_varlen */
+  int32_t max_q;         /* largest number of query tokens of a sequence in this step (0: max_s) */
+  int32_t _pad3;
 } B200LlamaStep;
 
 int b200_llama_embed(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream);

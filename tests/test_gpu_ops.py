@@ -193,6 +193,37 @@ def test_attn_prefill_varlen(ops, h, kv, d, causal):
     _close(got, ref, rel=2e-3, what=f"attn_prefill h{h} kv{kv} d{d} causal={causal}")
 
 
+@pytest.mark.parametrize("h,kv,d", [(4, 4, 128), (8, 2, 128), (8, 2, 64), (4, 1, 128)])
+def test_attn_prefill_paged_with_cached_context(ops, h, kv, d):
+    """tcgen05 / TMA prefill attention through the block pool: every sequence has `past` cached tokens in front of `n_q` new
+    query tokens (past = 0: a plain prefill; n_q = 1: a decode row; ragged mixes of both, tile boundaries 127 / 128 / 129, a
+    context that ends in the middle of a page).  Oracle: causal attention over the whole sequence, rows of the new tokens."""
+    cases = [(0, 1), (0, 127), (0, 128), (0, 129), (0, 300), (5, 60), (100, 1), (128, 128), (200, 57), (1000, 40), (17, 260)]
+    lens = [p + n for p, n in cases]
+    _, ks, vs, k_pool, v_pool, bt = _paged_case(ops, lens, h, kv, d, seed=3 * h + d)
+    g = torch.Generator().manual_seed(99)
+    scale = d ** -0.5
+    qs, refs, cu = [], [], [0]
+    for (past, n_q), k, v in zip(cases, ks, vs):
+        L = past + n_q
+        q_full = torch.randn(L, h, d, generator=g).half()
+        ref_full = oll.attention_prefill(q_full, k, v, [0, L], scale)
+        qs.append(q_full[past:])
+        refs.append(ref_full[past:])
+        cu.append(cu[-1] + n_q)
+    q = torch.cat(qs)
+    T = q.shape[0]
+    qkv = torch.zeros(T, (h + 2 * kv) * d, dtype=torch.float16)
+    qkv[:, :h * d] = q.reshape(T, -1)
+    qkv_d = qkv.to(DEV)
+    got = ops.attn_prefill_paged(qkv_d[:, :h * d].view(T, h, d), k_pool, v_pool, bt.to(DEV), torch.tensor(lens, dtype=torch.int32, device=DEV),
+                                 torch.tensor(cu, dtype=torch.int32, device=DEV), max(n for _, n in cases), scale)
+    torch.cuda.synchronize()
+    ref = torch.cat(refs)
+    for b, (past, n_q) in enumerate(cases):  # per sequence, so a failure names the case
+        _close(got[cu[b]:cu[b + 1]], ref[cu[b]:cu[b + 1]], rel=2e-3, what=f"attn_prefill_paged h{h} kv{kv} d{d} past={past} n_q={n_q}")
+
+
 def test_masked_softmax_and_fused_attention(ops):
     """b200_masked_softmax vs the restated semantics of forward_masked_softmax_kernel (custom_kernels/fused_attention_cuda.cu:28-107):
     fp32 softmax over unmasked positions, masked -> 0, all-masked row -> zeros; kv beyond the reference's 4096 limit; and the

@@ -80,3 +80,34 @@ def test_router_style_session_over_uds(tmp_path):
     for i in (0, 1, 2):
         n = min(len(got[i]), n_ex[i])
         assert n >= 2 and got[i][:n] == ref[i][:n], f"request {i}: {got[i]} vs oracle {ref[i]}"
+
+
+@pytest.mark.parametrize("quantize", [None, "gptq"])
+def test_continuous_batching_session_matches_oracle(tmp_path, quantize):
+    """BASELINE config[4] in miniature: Poisson arrivals, ragged prompts and output lengths, at most 4 running requests, driven
+    through Prefill (with to_prune) / NextToken (several cached batch ids -> concatenate, completed ids -> prune) by the router
+    stand-in that bench.py's `*-mixed` workloads use.  Every request must receive exactly the tokens the oracle generates for it
+    alone (outside the tie band): batching, pruning and concatenation change no result; every block returns to the pool."""
+    from tgis_b200 import pb
+    from tgis_b200.server import Cache, TextGenerationService
+    from tests.test_gpu_generate import _text
+    from tools import router_sim
+
+    model, oracle, tok = _setup(tmp_path, quantize)
+    mgr = model.kv_cache_manager
+    service = TextGenerationService(model, Cache(), ["unix:///dev/null"])
+    reqs = router_sim.make_requests(14, rate_per_s=400.0, prompt_range=(3, 40), new_range=(2, 10), vocab=512, seed=1)
+    with torch.inference_mode():
+        out = router_sim.run_session(service, pb, reqs, max_batch_size=4, text_of=_text, sync=torch.cuda.synchronize)
+    st = out["stats"]
+    assert st["prefill_calls"] >= 4 and st["concat_steps"] >= 2 and st["max_batch"] == 4, st
+    assert mgr.free_blocks == mgr.total_num_gpu_blocks
+    checked = 0
+    for r in reqs:
+        got = out["tokens"][r.id]
+        assert len(got) == r.max_new
+        ref, n_ex = _oracle_tokens(oracle, [r.prompt], r.max_new)
+        n = min(len(got), n_ex[0])
+        assert got[:n] == ref[0].tolist()[:n], f"request {r.id}: {got} vs oracle {ref[0].tolist()}"
+        checked += n
+    assert checked >= 40

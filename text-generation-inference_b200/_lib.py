@@ -38,6 +38,7 @@ SIGNATURES = {
     "b200_attn_decode_workspace_bytes": (_L, [_I, _I, _I, _I]),
     "b200_attn_decode_paged": (_I, [_P, _L, _P, _P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "b200_attn_prefill_varlen": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _P]),
+    "b200_attn_prefill_paged": (_I, [_P, _L, _L, _P, _P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "b200_gemm_workspace_bytes": (_L, [_L, _L, _L]),
     "b200_gemm_workspace_bytes_max": (_L, [_L, _L]),
     "b200_gemm_f16": (_I, [_P, _P, _P, _P, _L, _L, _L, _P, _P]),
@@ -88,7 +89,8 @@ class B200LlamaStep(ctypes.Structure):
                 ("kv_layer_stride_bytes", _L), ("kv_v_offset_bytes", _L), ("hidden", _P), ("residual", _P), ("normed", _P),
                 ("qkv", _P), ("attn_out", _P), ("gate_up", _P), ("act", _P), ("perm_x", _P), ("attn_ws", _P), ("attn_ws_bytes", _L),
                 ("gemm_ws", _P), ("head_rows", _P), ("n_head_rows", _L), ("head_in", _P), ("logits", _P), ("next_ids", _P), ("banned_ids", _P),
-                ("defer_splitk", ctypes.c_int32), ("_pad2", ctypes.c_int32), ("p2p_norm", _P), ("p2p_argmax", _P)]
+                ("defer_splitk", ctypes.c_int32), ("_pad2", ctypes.c_int32), ("p2p_norm", _P), ("p2p_argmax", _P),
+                ("kv_num_blocks", _L), ("max_q", ctypes.c_int32), ("_pad3", ctypes.c_int32)]
 
 
 _WP, _SP, _KP = ctypes.POINTER(B200LlamaWeights), ctypes.POINTER(B200LlamaStep), ctypes.POINTER(B200SplitK)

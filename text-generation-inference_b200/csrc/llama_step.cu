@@ -115,7 +115,12 @@ static int attn_body(const B200LlamaWeights* w, const B200LlamaStep* s, int laye
                                  w->n_kv_heads, d, stream));
   }
   const int64_t qkv_stride = (int64_t)(w->n_heads + 2 * w->n_kv_heads) * d;
-  if (s->is_prefill) {
+  if (s->is_prefill && s->kv_num_blocks > 0 && s->block_table && s->context_lens) {
+    // through the pool (the step's K / V were just appended): tcgen05 + TMA, and the queries may follow a cached context
+    RUN(b200_attn_prefill_paged(s->qkv, qkv_stride, T, k_pool, v_pool, s->kv_num_blocks, s->block_table, s->block_table_stride,
+                                s->context_lens, s->cu_seqlens, s->attn_out, (int64_t)w->n_heads * d, s->B,
+                                s->max_q > 0 ? s->max_q : s->max_s, w->n_heads, w->n_kv_heads, d, w->softmax_scale, stream));
+  } else if (s->is_prefill) {
     const __half* q = (const __half*)s->qkv;
     RUN(b200_attn_prefill_varlen(q, qkv_stride, q + (int64_t)w->n_heads * d, qkv_stride,
                                  q + (int64_t)(w->n_heads + w->n_kv_heads) * d, qkv_stride, s->cu_seqlens, s->attn_out,

@@ -194,6 +194,7 @@ class FlashLlamaForCausalLM(nn.Module):
         self._all_reduce = LayerBoundaryAllReduce(self.process_group)
         self._boundary = FusedBoundary(self.process_group, config.hidden_size)
         self.defer_splitk = __import__("os").environ.get("B200_DEFER_SPLITK", "1") != "0"
+        self.prefill_paged = __import__("os").environ.get("B200_PREFILL_PAGED", "1") != "0"
 
     def get_input_embeddings(self) -> nn.Module:
         return self.model.embed_tokens
@@ -277,6 +278,11 @@ class FlashLlamaForCausalLM(nn.Module):
         s.next_ids = next_ids.data_ptr() if next_ids is not None else None
         s.defer_splitk = int(self.defer_splitk)
         s.p2p_norm, s.p2p_argmax = self._boundary.norm, self._boundary.argmax
+        # prefill attends through the block pool (tcgen05 + TMA, csrc/attn_prefill_paged.cu): the step's K / V are appended first,
+        # so the same kernel serves prompts that follow a cached context.  B200_PREFILL_PAGED=0: the varlen HMMA kernel on fresh q/k/v.
+        if is_prefill and self.prefill_paged and kv.block_table is not None and kv.block_table.numel() > 0:
+            s.kv_num_blocks = mgr.pool.shape[2]
+            s.max_q = int(max_s)
         return s
 
     @property

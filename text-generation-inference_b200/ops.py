@@ -168,6 +168,26 @@ def attn_prefill_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_se
     return out
 
 
+def attn_prefill_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_table: torch.Tensor,
+                       context_lens: torch.Tensor, cu_seqlens_q: torch.Tensor, max_q: int, softmax_scale: float,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [T_q, h, d] (a strided view of the fused qkv activation is fine); pools [num_blocks, n_kv, 16, d] already holding this
+    step's K / V; context_lens [B] include them.  Causal over absolute positions (queries may follow a cached context)."""
+    _req(q, torch.float16, "q")
+    _req(block_table, torch.int32, "block_table")
+    _req(context_lens, torch.int32, "context_lens")
+    _req(cu_seqlens_q, torch.int32, "cu_seqlens_q")
+    T, h, d = q.shape
+    assert q.stride(2) == 1 and q.stride(1) == d and k_pool.is_contiguous() and v_pool.is_contiguous()
+    if out is None:
+        out = torch.empty(T, h, d, dtype=torch.float16, device=q.device)
+    _lib.check(_lib.load().b200_attn_prefill_paged(_ptr(q), q.stride(0), T, _ptr(k_pool), _ptr(v_pool), k_pool.shape[0], _ptr(block_table),
+                                                   block_table.stride(0), _ptr(context_lens), _ptr(cu_seqlens_q), _ptr(out),
+                                                   out.stride(0), cu_seqlens_q.shape[0] - 1, int(max_q), h, k_pool.shape[1], d,
+                                                   float(softmax_scale), _stream()), "attn_prefill_paged")
+    return out
+
+
 _gemm_ws = {}
 
 
