@@ -299,9 +299,7 @@ def measure_workload(args, workload, world, rank, full: bool):
         batch.input_ids.copy_(torch.tensor([t.token_id for t in toks], dtype=torch.int64))
 
         def device_step(use_graph=True):
-            model._run_fused_step(batch, st, use_graph)
-            batch.position_ids += 1
-            batch.input_ids.copy_(st["next_ids"])
+            model._run_fused_step(batch, st, use_graph)  # chains the chosen ids into input_ids on the device
 
         for _ in range(W):
             device_step()
@@ -351,7 +349,6 @@ def measure_workload(args, workload, world, rank, full: bool):
             batch.input_lengths[i] += skipped
             batch.next_token_chooser.current_tokens[i] += skipped
         batch.max_seqlen += skipped
-        batch.cu_seqlens.add_(batch.cu_seqlens_q * skipped)
         # graph replays launch the same kernels as an eager step; count them from one eager step's counter delta
         l0 = lib.b200_launch_count()
         device_step(use_graph=False)
@@ -362,7 +359,6 @@ def measure_workload(args, workload, world, rank, full: bool):
             batch.input_lengths[i] += 1
             batch.next_token_chooser.current_tokens[i] += 1
         batch.max_seqlen += 1
-        batch.cu_seqlens.add_(batch.cu_seqlens_q)
 
         # ---- e2e, second half of the trajectory: up to the last token the requests asked for
         toks = model.generate_token(batch)[0]

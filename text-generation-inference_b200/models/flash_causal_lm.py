@@ -272,7 +272,7 @@ class FlashCausalLM(Model):
             if kv.slot_mapping.shape[0] < B:
                 kv.slot_mapping = torch.empty(B, dtype=torch.int64, device=self.device)
             if self._can_fuse_greedy(batch):
-                generated, errs, forward_time_ns = self._decode_fused_greedy(batch)
+                generated, errs, forward_time_ns = self._decode_fused_greedy(batch)  # advances cu_seqlens inside the step
             else:
                 self._decode_advance(batch)
                 start_time = time.time_ns()
@@ -280,8 +280,10 @@ class FlashCausalLM(Model):
                                             batch.max_seqlen, None, kv, None, None)
                 forward_time_ns = time.time_ns() - start_time
                 generated, errs = self._process_decode(batch, out)
+                batch.cu_seqlens.add_(batch.cu_seqlens_q)
             input_infos = None
-        batch.cu_seqlens.add_(batch.cu_seqlens_q)
+        if first:
+            batch.cu_seqlens.add_(batch.cu_seqlens_q)
         batch.max_seqlen += 1
         return generated, input_infos, errs, forward_time_ns
 
@@ -308,7 +310,8 @@ class FlashCausalLM(Model):
         kv, B = batch.past_key_values, len(batch)
         chooser = batch.next_token_chooser
         key = (batch.input_ids.data_ptr(), batch.position_ids.data_ptr(), kv.block_table.data_ptr(), kv.context_lens.data_ptr(),
-               kv.slot_mapping.data_ptr(), B, self.model.scratch.version)
+               kv.slot_mapping.data_ptr(), batch.all_input_ids_tensor.data_ptr(), batch.cu_seqlens.data_ptr(), B,
+               self.model.scratch.version)
         st = getattr(batch, "_fused", None)
         if st is None or st["key"] != key:
             V = self.model.lm_head.linear.weight.shape[0]
@@ -342,20 +345,16 @@ class FlashCausalLM(Model):
         start_time = time.time_ns()
         self._run_fused_step(batch, st)
         forward_time_ns = time.time_ns() - start_time
-        batch.position_ids += 1
-        next_ids = st["next_ids"]
-        batch.input_ids.copy_(next_ids)
-        batch.all_input_ids_tensor.scatter_(dim=1, index=batch.position_ids[:, None], src=next_ids[:, None])
-        generated = []
-        for i, (r, tok) in enumerate(zip(batch.requests, next_ids.tolist())):  # the step's one D2H read
-            generated.append(TokenInfo(request_id=r.id, token_id=tok))
-            batch.input_lengths[i] += 1
+        ids = st["next_ids"].tolist()  # the step's one D2H read
+        generated = [TokenInfo(request_id=r.id, token_id=tok) for r, tok in zip(batch.requests, ids)]
+        batch.input_lengths = [n + 1 for n in batch.input_lengths]
         st["steps"] += 1
         return generated, [], forward_time_ns
 
     def _run_fused_step(self, batch, st, use_graph: bool = True) -> None:
-        """decode_advance (+ device-to-device token chaining) and the whole model step; replayed as a CUDA graph from
-        the third step of a stable batch on."""
+        """decode_advance, the whole model step and the batch's device-side bookkeeping for the next step (position_ids,
+        input_ids <- chosen ids, all_input_ids_tensor, cu_seqlens: flash_causal_lm.py:457-458, 533-535 of the reference);
+        replayed as ONE CUDA graph from the third step of a stable batch on."""
         kv, B = batch.past_key_values, len(batch)
         lib = _lib.load()
         s = st["step"]
@@ -377,6 +376,10 @@ class FlashCausalLM(Model):
                     ops.argmax(st["full"], st["banned"], out=st["next_ids"])
                 else:
                     ops.argmax(st["logits"], st["banned"], out=st["next_ids"])
+            batch.position_ids.add_(1)
+            batch.input_ids.copy_(st["next_ids"])
+            batch.all_input_ids_tensor.scatter_(dim=1, index=batch.position_ids[:, None], src=st["next_ids"][:, None])
+            batch.cu_seqlens.add_(batch.cu_seqlens_q)
 
         if use_graph and st["steps"] >= 2 and USE_CUDA_GRAPHS:
             g = torch.cuda.CUDAGraph()

@@ -128,6 +128,9 @@ def argmax(logits: torch.Tensor, banned_ids: Optional[torch.Tensor] = None, out:
     return out
 
 
+_attn_ws = {}
+
+
 def attn_decode_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_table: torch.Tensor,
                       context_lens: torch.Tensor, max_context_len: int, softmax_scale: float, n_kv_heads: int,
                       out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -141,8 +144,13 @@ def attn_decode_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tenso
         out = torch.empty(B, h, d, dtype=torch.float16, device=q.device)
     lib = _lib.load()
     need = lib.b200_attn_decode_workspace_bytes(B, h, d, max_context_len)
-    if workspace is None or workspace.numel() * workspace.element_size() < need:
-        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
+    if workspace is None:  # per-device grow-only workspace; its arrival counters (front 64 KiB) start at zero and re-arm themselves
+        workspace = _attn_ws.get(q.device)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.zeros(max(need, 1 << 22), dtype=torch.uint8, device=q.device)
+            _attn_ws[q.device] = workspace
+    elif workspace.numel() * workspace.element_size() < need:
+        raise _lib.B200Error("attn_decode_paged: workspace too small")
     _lib.check(lib.b200_attn_decode_paged(_ptr(q), q.stride(0), _ptr(k_pool), _ptr(v_pool), _ptr(block_table),
                                           block_table.stride(0), _ptr(context_lens), _ptr(out), out.stride(0), _ptr(workspace),
                                           workspace.numel() * workspace.element_size(), B, h, n_kv_heads, d, max_context_len,

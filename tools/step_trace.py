@@ -41,8 +41,6 @@ def main():
 
         def step(use_graph):
             model._run_fused_step(batch, st, use_graph)
-            batch.position_ids += 1
-            batch.input_ids.copy_(st["next_ids"])
 
         # untraced graph-replayed step time
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
