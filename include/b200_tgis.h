@@ -110,9 +110,7 @@ int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int6
  * (utils/flash_attn.py:43-127 <- flash_llama_modeling.py:285-295) and fms-extras paged_attention
  * (paged_llama_modeling.py:267).  q: one token per sequence, head-major [n_heads][d] at q + b*q_token_stride (halves).
  * block_table[b][i] = pool block of the i-th 16-token page; context_lens[b] includes the token just written.
- * out[b] at out + b*out_token_stride.  workspace >= b200_attn_decode_workspace_bytes(...); its first 64 KiB (split-KV arrival
- * counters: the last chunk of a (sequence, kv head) to finish merges the partials, no separate combine launch) must have been
- * zeroed once, the kernel re-arms them. */
+ * out[b] at out + b*out_token_stride.  workspace >= b200_attn_decode_workspace_bytes(...). */
 int64_t b200_attn_decode_workspace_bytes(int B, int n_heads, int head_dim, int max_context_len);
 int b200_attn_decode_paged(const void* q, int64_t q_token_stride, const void* k_pool, const void* v_pool,
                            const int32_t* block_table, int64_t block_table_stride, const int32_t* context_lens, void* out,

@@ -308,10 +308,14 @@ class LlamaOracle:
         return logits, kv
 
     # -- greedy generate (Greedy chooser, utils/tokens.py:44-46) ----------------------
-    def generate_greedy(self, prompts: List[List[int]], n_new: int, banned_token: Optional[int] = None):
+    def generate_greedy(self, prompts: List[List[int]], n_new: int, banned_token: Optional[int] = None,
+                        forced: Optional[torch.Tensor] = None, keep_logits: bool = True, on_step=None):
         """Returns (tokens [B, n_new], logits list per step). Mirrors FlashCausalLM.generate_token's
         loop (models/flash_causal_lm.py:405-460): prefill then n_new-1 decode steps.
-        banned_token: min_new_tokens EOS mask, `scores[idx, eos] = -inf` before the arg-max (utils/tokens.py:244-246)."""
+        banned_token: min_new_tokens EOS mask, `scores[idx, eos] = -inf` before the arg-max (utils/tokens.py:244-246).
+        forced [B, n_new] (optional): teacher forcing - the returned tokens are still this oracle's own choices, but step t + 1 is
+        fed forced[:, t], so a long trajectory produced elsewhere can be checked token by token without diverging after a tie.
+        on_step(step, logits) (optional) is called with every step's logits (use it with keep_logits=False on long runs)."""
         def choose(lg):
             lg = lg.float().clone()
             if banned_token is not None:
@@ -325,16 +329,22 @@ class LlamaOracle:
         pos = torch.cat([torch.arange(len(p)) for p in prompts])
         logits, kv = self.forward(ids, pos, cu, None, prefill=True)
         lens = [len(p) for p in prompts]
-        toks, all_logits = [], [logits]
+        toks, all_logits = [], ([logits] if keep_logits else [])
+        if on_step:
+            on_step(0, logits)
         nxt = choose(logits)
         toks.append(nxt)
-        for _ in range(n_new - 1):
+        for step in range(1, n_new):
             pos = torch.tensor(lens, dtype=torch.long)
-            logits, kv = self.forward(nxt, pos, list(range(len(prompts) + 1)), kv, prefill=False)
+            fed = nxt if forced is None else forced[:, step - 1].to(torch.long)
+            logits, kv = self.forward(fed, pos, list(range(len(prompts) + 1)), kv, prefill=False)
             lens = [l + 1 for l in lens]
             nxt = choose(logits)
             toks.append(nxt)
-            all_logits.append(logits)
+            if keep_logits:
+                all_logits.append(logits)
+            if on_step:
+                on_step(step, logits)
         return torch.stack(toks, 1), all_logits
 
 

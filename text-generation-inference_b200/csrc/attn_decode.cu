@@ -39,8 +39,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 2)
 attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, const __half* __restrict__ k_pool,
                          const __half* __restrict__ v_pool, const int32_t* __restrict__ block_table, int64_t bt_stride,
                          const int32_t* __restrict__ context_lens, float* __restrict__ part_o, float* __restrict__ part_ml,
-                         int* __restrict__ counters, __half* __restrict__ out, int64_t out_token_stride, int n_heads, int n_kv,
-                         int n_chunks_max, int chunk_tokens, float scale_log2) {
+                         int n_heads, int n_kv, int n_chunks_max, int chunk_tokens, float scale_log2) {
   using S = DecodeSmem<D>;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stages = smem;
@@ -52,19 +51,12 @@ attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, c
   const int chunk = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int L = context_lens[b];
   const int tok0 = chunk * chunk_tokens;
-  const int G = n_heads / n_kv;
-  if (tok0 >= L) {
-    // nothing to attend in this chunk; a padding row (context <= 0) gets a zero output from its first chunk's CTA
-    if (chunk == 0)
-      for (int idx = threadIdx.x; idx < G * D; idx += kDecodeThreads) out[(int64_t)b * out_token_stride + hk * G * D + idx] = __float2half_rn(0.f);
-    return;
-  }
+  if (tok0 >= L) return;
   const int n_tok = min(chunk_tokens, L - tok0);
   const int n_pages = (n_tok + kPageTokens - 1) / kPageTokens;
   const int n_iters = (n_pages + kPagesPerStage - 1) / kPagesPerStage;
-  const int n_active = (L + chunk_tokens - 1) / chunk_tokens;  // chunks of this sequence that hold tokens
+  const int G = n_heads / n_kv;
   const int warp = warp_id(), lane = lane_id();
-  __shared__ int s_last;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::kStages; ++s) {
@@ -218,7 +210,6 @@ attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, c
     if (tig == 0) { mml[(warp * 16 + g + 8) * 2] = m1; mml[(warp * 16 + g + 8) * 2 + 1] = l1; }
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32));
-  const bool single = n_active == 1;  // the only chunk of its sequence: the merged result is final
   for (int idx = threadIdx.x; idx < G * D; idx += kConsumerWarps * 32) {
     const int r = idx / D, d = idx % D;
     float M = kNegBig;
@@ -231,53 +222,40 @@ attn_decode_paged_kernel(const __half* __restrict__ q, int64_t q_token_stride, c
       acc += f * mo[(w * 16 + r) * S::kMergeStride + d];
       lsum += f * mml[(w * 16 + r) * 2 + 1];
     }
-    if (single) {
-      out[(int64_t)b * out_token_stride + (hk * G + r) * D + d] = __float2half_rn(acc / lsum);
-    } else {
-      const int64_t slot = ((int64_t)b * n_heads + hk * G + r) * n_chunks_max + chunk;
-      part_o[slot * D + d] = acc;
-      if (d == 0) { part_ml[slot * 2] = M; part_ml[slot * 2 + 1] = lsum; }
-    }
+    const int64_t slot = ((int64_t)b * n_heads + hk * G + r) * n_chunks_max + chunk;
+    part_o[slot * D + d] = acc;
+    if (d == 0) { part_ml[slot * 2] = M; part_ml[slot * 2 + 1] = lsum; }
   }
-  if (single) return;
-  // split-KV merge by the last chunk of this (sequence, kv head) to finish (no separate combine launch): partials -> gpu-scope
-  // fence -> arrival counter; the CTA that observes every other chunk's arrival re-arms the counter and merges all of them
-  __threadfence();
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
-  if (threadIdx.x == 0) {
-    const int prev = atomicAdd(&counters[b * n_kv + hk], 1);
-    s_last = prev == n_active - 1;
-    if (s_last) counters[b * n_kv + hk] = 0;  // graph-replay safe
-    __threadfence();
+}
+
+template <int D>
+__global__ void attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                           const int32_t* __restrict__ context_lens, __half* __restrict__ out,
+                                           int64_t out_token_stride, int n_heads, int n_chunks_max, int chunk_tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const int L = context_lens[b];
+  const int nc = (L + chunk_tokens - 1) / chunk_tokens;
+  const int64_t base = ((int64_t)b * n_heads + head) * n_chunks_max;
+  float M = kNegBig;
+  for (int c = 0; c < nc; ++c) M = fmaxf(M, part_ml[(base + c) * 2]);
+  float acc = 0.f, l = 0.f;
+  for (int c = 0; c < nc; ++c) {
+    const float f = fast_exp2(part_ml[(base + c) * 2] - M);
+    acc += f * part_o[(base + c) * D + d];
+    l += f * part_ml[(base + c) * 2 + 1];
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
-  if (!s_last) return;
-  for (int idx = threadIdx.x; idx < G * D; idx += kConsumerWarps * 32) {
-    const int r = idx / D, d = idx % D;
-    const int64_t base = ((int64_t)b * n_heads + hk * G + r) * n_chunks_max;
-    float M = kNegBig;
-    for (int c = 0; c < n_active; ++c) M = fmaxf(M, __ldcg(&part_ml[(base + c) * 2]));
-    float acc = 0.f, lsum = 0.f;
-    for (int c = 0; c < n_active; ++c) {  // chunk order: the result does not depend on which CTA finished last
-      const float f = fast_exp2(__ldcg(&part_ml[(base + c) * 2]) - M);
-      acc += f * __ldcg(&part_o[(base + c) * D + d]);
-      lsum += f * __ldcg(&part_ml[(base + c) * 2 + 1]);
-    }
-    out[(int64_t)b * out_token_stride + (hk * G + r) * D + d] = __float2half_rn(acc / lsum);
-  }
+  out[(int64_t)b * out_token_stride + head * D + d] = __float2half_rn(nc > 0 ? acc / l : 0.f);
 }
 
 }  // namespace b200
 
 using namespace b200;
 
-// Workspace: 64 KiB of arrival counters (one per (sequence, kv head); ZERO before the first launch, the kernel re-arms them - the
-// caller allocates the workspace zeroed, like the GEMM workspace) followed by the fp32 split-KV partials, sized for the
-// smallest chunk.  The counters sit in front so that their place does not depend on the batch a launch serves.
-constexpr int64_t kDecodeCounterBytes = 64 * 1024;
 extern "C" int64_t b200_attn_decode_workspace_bytes(int B, int n_heads, int head_dim, int max_context_len) {
-  const int64_t nc = (max_context_len + kMinChunkTokens - 1) / kMinChunkTokens;
-  return kDecodeCounterBytes + (int64_t)B * n_heads * (nc > 0 ? nc : 1) * (head_dim + 2) * 4;
+  const int64_t nc = (max_context_len + kMinChunkTokens - 1) / kMinChunkTokens;  // sized for the smallest chunk
+  return (int64_t)B * n_heads * (nc > 0 ? nc : 1) * (head_dim + 2) * 4;
 }
 
 static int decode_num_sms() {
@@ -301,15 +279,17 @@ static int launch_decode(const void* q, int64_t q_token_stride, const void* k_po
     if (e != cudaSuccess) { b200_set_last_error(cudaGetErrorString(e)); return B200_ERR_CUDA; }
     configured = true;
   }
-  int* counters = reinterpret_cast<int*>(workspace);
-  float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kDecodeCounterBytes);
+  float* part_o = (float*)workspace;
   float* part_ml = part_o + (int64_t)B * n_heads * n_chunks * D;
   dim3 grid(n_chunks, n_kv, B);
   b200_timing_mark(B200_TIME_ATTN_DECODE, 0, st);
   B200_LAUNCH(attn_decode_paged_kernel<D>, grid, dim3(kDecodeThreads), (size_t)S::kBytes, st, (const __half*)q, q_token_stride,
-              (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o, part_ml, counters, (__half*)out,
-              out_token_stride, n_heads, n_kv, n_chunks, chunk_tokens, scale * 1.4426950408889634f);
+              (const __half*)k_pool, (const __half*)v_pool, block_table, bt_stride, context_lens, part_o, part_ml, n_heads, n_kv,
+                n_chunks, chunk_tokens, scale * 1.4426950408889634f);
   b200_timing_mark(B200_TIME_ATTN_DECODE, 1, st);
+  b200_count_launches(1);
+  B200_LAUNCH(attn_decode_combine_kernel<D>, dim3(n_heads, B), dim3(D), 0, st, (const float*)part_o, (const float*)part_ml, context_lens,
+              (__half*)out, out_token_stride, n_heads, n_chunks, chunk_tokens);
   b200_count_launches(1);
   return B200_OK;
 }
@@ -324,7 +304,6 @@ extern "C" int b200_attn_decode_paged(const void* q, int64_t q_token_stride, con
     b200_set_last_error("attn_decode_paged: need n_heads % n_kv_heads == 0 and group size <= 16");
     return B200_ERR_ARG;
   }
-  if ((int64_t)B * n_kv_heads * 4 > kDecodeCounterBytes) { b200_set_last_error("attn_decode_paged: B * n_kv_heads > 16384"); return B200_ERR_ARG; }
   if (workspace_bytes < b200_attn_decode_workspace_bytes(B, n_heads, head_dim, max_context_len)) {
     b200_set_last_error("attn_decode_paged: workspace too small");
     return B200_ERR_ARG;

@@ -173,7 +173,7 @@ class StepScratch:
                 self.version += 1
         need = _lib.load().b200_attn_decode_workspace_bytes(max(B, 1), m.model.num_heads, m.model.head_size, max(max_ctx, 1))
         if self.attn_ws is None or self.attn_ws.numel() < need:
-            self.attn_ws = torch.zeros(need, dtype=torch.uint8, device=dev)  # arrival counters in front start at zero
+            self.attn_ws = torch.empty(need, dtype=torch.uint8, device=dev)
             self.version += 1
 
 

@@ -144,7 +144,7 @@ def attn_decode_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tenso
         out = torch.empty(B, h, d, dtype=torch.float16, device=q.device)
     lib = _lib.load()
     need = lib.b200_attn_decode_workspace_bytes(B, h, d, max_context_len)
-    if workspace is None:  # per-device grow-only workspace; its arrival counters (front 64 KiB) start at zero and re-arm themselves
+    if workspace is None:  # per-device grow-only workspace
         workspace = _attn_ws.get(q.device)
         if workspace is None or workspace.numel() < need:
             workspace = torch.zeros(max(need, 1 << 22), dtype=torch.uint8, device=q.device)

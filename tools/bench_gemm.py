@@ -39,7 +39,8 @@ def main():
             _lib.load().b200_debug_w4_flags(int(a.split("=")[1]))
             print("debug flags", a)
     shapes = [(64, 128, 128), (64, 128, 4096), (64, 4096, 128), (64, 4096, 4096), (64, 12288, 4096), (64, 22016, 4096), (64, 4096, 11008),
-              (1, 4096, 4096), (16, 4096, 4096), (256, 4096, 4096)]
+              (64, 6144, 4096), (64, 28672, 4096), (64, 4096, 14336), (64, 32000, 4096), (64, 128256, 4096),
+              (1, 4096, 4096), (16, 4096, 4096), (256, 4096, 4096), (4096, 4096, 4096)]
     for T, N, K in shapes:
         nbuf = max(1, min(8, int(300e6 // (N * K // 2 + 1))))
         x = torch.randn(T, K, device=dev).half()
@@ -57,7 +58,10 @@ def main():
         w = [torch.randn(N, K, device=dev).half() for _ in range(nbuf)]
         us = timeit(lambda i: ops.gemm_f16(x, w[i % nbuf], out=out))
         bytes_ = N * K * 2 + T * K * 2 + T * N * 2
-        print(f"f16   T={T:4d} N={N:6d} K={K:6d}: {us:8.1f} us  {bytes_ / us / 1e3:8.1f} GB/s")
+        # cuBLAS on the same shapes, same graph-replayed rotation over > L2 of weights (the library kernel to beat)
+        us_cublas = timeit(lambda i: torch.matmul(x, w[i % nbuf].t(), out=out))
+        print(f"f16   T={T:4d} N={N:6d} K={K:6d}: {us:8.1f} us  {bytes_ / us / 1e3:8.1f} GB/s   cuBLAS {us_cublas:8.1f} us  "
+              f"{bytes_ / us_cublas / 1e3:8.1f} GB/s   ratio {us_cublas / us:5.2f}x")
         del w
 
 
