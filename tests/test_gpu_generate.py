@@ -211,3 +211,59 @@ def test_prompt_prefix_equals_the_same_tokens_typed_in(tmp_path):
             out = model.generate_token(batch)
     _assert_prefix_equal(got, ref.tolist(), n_exact, min_total=8)
     model.kv_cache_manager.free_sequences(batch.sequence_ids)
+
+
+def test_paged_convention_and_speculative_verification(tmp_path):
+    """The paged calling convention (paged_llama_modeling.py:443-462: forward(input_ids, position_ids, cache_data, ...)) on the same
+    kernels, and the verification forward of speculative decoding (models/paged_causal_lm.py:481-562): k candidate sequences per
+    parent, n tokens each, every token a row of the generation-form cache_data.  A candidate fed the true continuation must give,
+    token by token, the logits that plain one-token-at-a-time decoding gives; the acceptance rule keeps it and frees the rest."""
+    from tgis_b200.utils import paged
+
+    model, oracle, tok = _setup(tmp_path, None)
+    net, mgr = model.model, model.kv_cache_manager
+    prompts = _prompts(31, [7, 19, 33], 512)
+    n_spec = 4  # tokens verified per candidate: the last accepted one + 3 speculated
+    with torch.inference_mode():
+        # prefill through the paged convention
+        pos, cd = paged.prepare_inputs_for_prefill([len(p) for p in prompts], mgr)
+        ids = torch.tensor([t for p in prompts for t in p], dtype=torch.int64, device=DEV)
+        logits, embeds = net(ids, pos, cd, None, True)
+        last = (cd.context_lengths[1:] - 1).long()
+        assert embeds.shape == (ids.shape[0], net.config.hidden_size)
+        ref_tokens, ref_logits = oracle.generate_greedy(prompts, n_spec + 1, banned_token=None)
+        _logits_close(logits[last], ref_logits[0], "paged-convention prefill")
+        parents = cd.sequence_ids
+        first = logits[last].float().argmax(-1)
+        # plain decoding, one token per step, on CHILD copies so that the parents stay where they are
+        plain_ids = [mgr.add_child_sequences(p, 1)[0] for p in parents]
+        fed, plain_logits, chain = first, [], [first]
+        for _ in range(n_spec):
+            pos1, cd1 = paged.prepare_inputs_without_speculation(plain_ids, mgr)
+            lg = net(fed, pos1, cd1)
+            plain_logits.append(lg)
+            fed = lg.float().argmax(-1)
+            chain.append(fed)
+        mgr.free_sequences(plain_ids)
+        # speculative verification: candidate 0 = garbage, candidate 1 = the true continuation, in ONE forward
+        pos_s, cd_s, children = paged.prepare_candidates(parents, n_candidates=2, n_tokens=n_spec, kv_cache_manager=mgr)
+        truth = torch.stack(chain[:n_spec], 1)                                   # [B, n]: token fed at each of the n positions
+        garbage = truth.clone()
+        garbage[:, 1:] = (garbage[:, 1:] + 7) % 500 + 4
+        cand = torch.stack([garbage, truth], 1)                                  # [B, k, n]
+        lg_s = net(cand.reshape(-1), pos_s, cd_s).view(len(prompts), 2, n_spec, -1)
+        for j in range(n_spec):
+            _logits_close(lg_s[:, 1, j], plain_logits[j].cpu(), f"speculative row {j} vs plain decode step {j}")
+        survivors, accepted = paged.accept_candidates(cand.cpu(), lg_s.float().argmax(-1).cpu(), children, mgr)
+        for b, kids in enumerate(children):
+            assert survivors[b] == kids[1] and accepted[b] == [int(c[b]) for c in chain[1:n_spec + 1]]
+            assert mgr.sequence_length(kids[1]) == len(prompts[b]) + n_spec
+        mgr.free_sequences(survivors, recursive=True)
+    assert mgr.free_blocks == mgr.total_num_gpu_blocks
+
+
+def _logits_close(got, ref, what):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    tol = 4e-3 * ref.abs().max().item() + 2e-3
+    assert err.max().item() <= tol, f"{what}: max err {err.max().item():.4e} > {tol:.4e}"

@@ -323,3 +323,43 @@ def test_batch_bookkeeping_matches_reference_flash_causal_lm(mods):
     check("p1", C, toks)
     # the paged state agrees with the bookkeeping: context = tokens in cache, one slot per sequence for the next step
     assert C.past_key_values.context_lens.tolist() == [L - 1 for L in C.input_lengths]
+
+
+def test_speculation_hooks_of_the_kv_manager(mods):
+    """add_child_sequences / remove_tokens / recursive free (models/paged_causal_lm.py:481-562, utils/paged.py:185-203, 309-315 of the
+    reference; fms-extras semantics): candidates share their parent's blocks, the first write into a shared partial block copies it,
+    losers give everything back, the winner forgets its rejected tail, freeing the survivor recursively frees its ancestors."""
+    from tgis_b200.utils import paged
+    m = mods["Mgr"](num_layers=1, num_heads=2, emb_dim=128, kv_heads=2, device="cpu", total_num_gpu_blocks=16)
+    [parent] = m.allocate_tokens([20])
+    m.pool[:, :, m.sequence_blocks(parent)[1]] = 7.0
+    pos, cd, children = paged.prepare_candidates([parent], n_candidates=3, n_tokens=3, kv_cache_manager=m)
+    kids = children[0]
+    assert m.free_blocks == 11  # 2 parent blocks + one private copy of the partial block per child
+    assert all(m.sequence_blocks(k)[0] == m.sequence_blocks(parent)[0] for k in kids)
+    assert len({m.sequence_blocks(k)[1] for k in kids} | {m.sequence_blocks(parent)[1]}) == 4
+    assert float(m.pool[0, 0, m.sequence_blocks(kids[2])[1]].min()) == 7.0  # copy-on-write kept the parent's tokens
+    # generation form: one row per query token, contexts 21, 22, 23 for every candidate, slots 4..6 of its own block
+    assert pos.tolist() == [20, 21, 22] * 3 and cd.context_lengths.tolist() == [21, 22, 23] * 3
+    assert cd.block_mapping.shape == (9, 2) and cd.is_filled()
+    assert cd.slot_mapping.tolist() == [m.sequence_blocks(k)[1] * 16 + o for k in kids for o in (4, 5, 6)]
+    # candidate inputs: [last accepted token, 2 speculated]; candidate 1 speculated both right, candidate 0 one, candidate 2 none
+    fed = torch.tensor([[[5, 8, 3], [5, 8, 9], [5, 1, 1]]])
+    nxt = torch.tensor([[[8, 9, 4], [8, 9, 6], [8, 2, 2]]])
+    survivors, accepted = paged.accept_candidates(fed, nxt, children, m)
+    assert survivors == [kids[1]] and accepted == [[8, 9, 6]]
+    assert m.sequence_length(kids[1]) == 23 and m.free_blocks == 13
+    # a winner with a wrong tail forgets it
+    pos, cd, children = paged.prepare_candidates(survivors, n_candidates=2, n_tokens=4, kv_cache_manager=m)
+    fed = torch.tensor([[[6, 1, 1, 1], [6, 7, 1, 1]]])
+    nxt = torch.tensor([[[7, 2, 2, 2], [7, 2, 2, 2]]])
+    survivors, accepted = paged.accept_candidates(fed, nxt, children, m)
+    assert accepted == [[7, 2]] and m.sequence_length(survivors[0]) == 23 + 2
+    m.free_sequences(survivors, recursive=True)  # the survivor, its parent candidate and the original sequence (server.py:249)
+    assert m.free_blocks == 16
+    # prefill form
+    pos, cd = paged.prepare_inputs_for_prefill([3, 18], m)
+    assert not cd.is_filled() and cd.context_lengths.tolist() == [0, 3, 21] and pos.tolist() == [0, 1, 2] + list(range(18))
+    assert cd.slot_mapping.shape == (21,) and cd.block_mapping.shape == (2, 2)
+    pos, cd = paged.prepare_inputs_without_speculation(cd.sequence_ids, m)
+    assert pos.tolist() == [3, 18] and cd.context_lengths.tolist() == [4, 19]

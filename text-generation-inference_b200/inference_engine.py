@@ -55,8 +55,10 @@ class InferenceEngine:
         if model_type == "llama":
             if getattr(self._config, "tie_word_embeddings", False):
                 aliases = {"lm_head.weight": ["model.embed_tokens.weight"]}
-            from .models.custom_modeling.flash_llama_modeling import FlashLlamaForCausalLM
-            model_class = FlashLlamaForCausalLM
+            # one class serves both calling conventions of the reference (flash_llama_modeling.py / paged_llama_modeling.py;
+            # models/__init__.py:48-79 picks between them with PAGED_ATTENTION): the KV cache here is always paged
+            from .models.custom_modeling.paged_llama_modeling import PagedLlamaForCausalLM
+            model_class = PagedLlamaForCausalLM
         elif model_type == "gpt_neox":  # tgis_native.py:75-79
             from .models.custom_modeling.flash_neox_modeling import FlashGPTNeoXForCausalLM
             model_class = FlashGPTNeoXForCausalLM

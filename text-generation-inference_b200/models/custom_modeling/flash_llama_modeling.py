@@ -334,9 +334,14 @@ class FlashLlamaForCausalLM(nn.Module):
                            kv=past_key_values, cu_seqlens=cu_seqlens, head_rows=lm_head_indices, logits=logits,
                            inputs_embeds=inputs_embeds)
         self.run_step(s, embed=inputs_embeds is None)
-        if self.lm_head.should_gather:
-            world = self.process_group.size()
-            gathered = logits.new_empty(world, rows, V_local)
-            torch.distributed.all_gather_into_tensor(gathered, logits, group=self.process_group)
-            logits = gathered.permute(1, 0, 2).reshape(rows, world * V_local)
-        return logits, past_key_values
+        return self._gather_logits(logits), past_key_values
+
+    def _gather_logits(self, logits: torch.Tensor) -> torch.Tensor:
+        """vocab-sharded head: all-gather of this rank's [rows, V / tp] (utils/layers.py:249-269)"""
+        if not self.lm_head.should_gather:
+            return logits
+        world = self.process_group.size()
+        rows, V_local = logits.shape
+        gathered = logits.new_empty(world, rows, V_local)
+        torch.distributed.all_gather_into_tensor(gathered, logits, group=self.process_group)
+        return gathered.permute(1, 0, 2).reshape(rows, world * V_local)

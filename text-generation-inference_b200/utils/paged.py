@@ -35,6 +35,28 @@ class PagedKVState:
     max_blocks: int
 
 
+@dataclass
+class PagedAttentionCacheData:
+    """What fms-extras' `allocate_tokens` hands to the paged model classes (read at utils/paged.py:92-159, :194-257 and
+    paged_llama_modeling.py:388-423 of the reference): per-step index tensors over the block pool.
+    Prefill form: `context_lengths` = cumulative sequence lengths [B + 1] (utils/paged.py:148-157).  Generation form: one row per
+    query TOKEN - `block_mapping` [T, max_blocks], `context_lengths` [T] = keys that token attends (itself included), so the n
+    tokens of a speculative candidate are n rows over the same blocks with contexts L - n + 1 .. L (utils/paged.py:109-134, 230-241)."""
+    sequence_ids: List[int]
+    slot_mapping: torch.Tensor          # [T] int64 after flattening ([B, n] as allocated)
+    block_mapping: torch.Tensor         # int32
+    context_lengths: torch.Tensor       # int32
+    position_ids: torch.Tensor          # int64
+    max_sequence_length: int
+    query_length: int
+    is_generating: bool
+    unflatten_indices: Optional[torch.Tensor] = None
+    flatten_indices: Optional[torch.Tensor] = None
+
+    def is_filled(self) -> bool:
+        return self.is_generating
+
+
 class PagedKVCacheManager:
     def __init__(self, num_layers: int, num_heads: int, emb_dim: int, kv_heads: int = 0, tensor_parallel_size: int = 1,
                  dtype: torch.dtype = torch.float16, device="cuda", total_num_gpu_blocks: Optional[int] = None,
@@ -65,6 +87,9 @@ class PagedKVCacheManager:
         self._blocks: Dict[int, List[int]] = {}
         self._lens: Dict[int, int] = {}
         self._next_id = 0
+        # speculative decoding (models/paged_causal_lm.py:481-562): candidate sequences share their parent's blocks
+        self._refs: Dict[int, int] = {}     # block id -> sequences holding it (absent = 1)
+        self._parent: Dict[int, int] = {}   # child sequence id -> parent sequence id
 
     def block_bytes(self) -> int:
         """bytes of one 16-token block across all layers, K and V (get_kv_cache_block_size * n_layers * dtype size)."""
@@ -105,9 +130,18 @@ class PagedKVCacheManager:
         return list(buf)
 
     def _release(self, ids: List[int]) -> None:
-        if ids:
-            buf = (ctypes.c_int32 * len(ids))(*ids)
-            _lib.check(_lib.load().b200_kv_alloc_release(self._alloc, buf, len(ids)), "kv_alloc_release")
+        """drops one reference of every block; blocks nobody holds any more go back to the allocator"""
+        free = []
+        for b in ids:
+            n = self._refs.get(b, 1) - 1
+            if n <= 0:
+                self._refs.pop(b, None)
+                free.append(b)
+            else:
+                self._refs[b] = n
+        if free:
+            buf = (ctypes.c_int32 * len(free))(*free)
+            _lib.check(_lib.load().b200_kv_alloc_release(self._alloc, buf, len(free)), "kv_alloc_release")
 
     def blocks_needed(self, num_tokens: int) -> int:
         return (num_tokens + self.block_size - 1) // self.block_size
@@ -125,13 +159,22 @@ class PagedKVCacheManager:
             have_len, have_blocks = (0, 0) if new else (self._lens[sid], len(self._blocks[sid]))
             target = have_len + n + (reserve_tokens[i] if reserve_tokens else 0)
             need.append(max(0, self.blocks_needed(target) - have_blocks))
-        got = self._take(sum(need))  # all or nothing
+        # a sequence that is about to write into a block it shares with its parent / siblings gets its own copy first
+        cow = [] if new else [sid for sid, n in zip(sequence_ids, num_tokens_per_sequence)
+                              if n > 0 and self._lens[sid] % self.block_size != 0 and self._refs.get(self._blocks[sid][-1], 1) > 1]
+        got = self._take(sum(need) + len(cow))  # all or nothing
         if new:
             for sid in sequence_ids:
                 self._blocks[sid] = []
                 self._lens[sid] = 0
             self._next_id += len(sequence_ids)
         pos = 0
+        for sid in cow:
+            old, fresh = self._blocks[sid][-1], got[pos]
+            pos += 1
+            self.pool[:, :, fresh].copy_(self.pool[:, :, old])
+            self._blocks[sid][-1] = fresh
+            self._release([old])
         for sid, n, k in zip(sequence_ids, num_tokens_per_sequence, need):
             self._blocks[sid].extend(got[pos:pos + k])
             pos += k
@@ -139,11 +182,63 @@ class PagedKVCacheManager:
         return sequence_ids
 
     def free_sequences(self, sequence_ids: List[int], recursive: bool = False) -> None:
+        """recursive: also the chain of parents a speculative sequence descends from (server.py:249)."""
         for sid in sequence_ids:
-            blocks = self._blocks.pop(sid, None)
-            self._lens.pop(sid, None)
-            if blocks:
-                self._release(blocks)
+            while sid is not None:
+                blocks = self._blocks.pop(sid, None)
+                self._lens.pop(sid, None)
+                if blocks:
+                    self._release(blocks)
+                sid = self._parent.pop(sid, None) if recursive else None
+
+    def add_child_sequences(self, parent_sequence_id: int, num_children: int) -> List[int]:
+        """`num_children` candidate sequences that start as copies of the parent (utils/paged.py:194-203 of the reference): they
+        reference the parent's blocks; the first token a child appends to a shared partial block copies that block."""
+        blocks, length = self._blocks[parent_sequence_id], self._lens[parent_sequence_id]
+        used = blocks[:self.blocks_needed(length)]  # reserved-but-empty tail blocks stay with the parent
+        children = list(range(self._next_id, self._next_id + num_children))
+        self._next_id += num_children
+        for cid in children:
+            self._blocks[cid] = list(used)
+            self._lens[cid] = length
+            self._parent[cid] = parent_sequence_id
+            for b in used:
+                self._refs[b] = self._refs.get(b, 1) + 1
+        return children
+
+    def remove_tokens(self, sequence_id: int, num_tokens: int) -> None:
+        """forgets the last `num_tokens` tokens of a sequence (rejected speculative tokens, utils/paged.py:309-315): the
+        context shrinks, blocks that no longer hold a token are given back; the slots are simply overwritten later."""
+        if num_tokens <= 0:
+            return
+        new_len = self._lens[sequence_id] - num_tokens
+        if new_len < 0:
+            raise ValueError(f"remove_tokens: sequence {sequence_id} has {self._lens[sequence_id]} tokens")
+        keep = self.blocks_needed(new_len)
+        drop = self._blocks[sequence_id][keep:]
+        del self._blocks[sequence_id][keep:]
+        self._lens[sequence_id] = new_len
+        self._release(drop)
+
+    def cache_data(self, sequence_ids: List[int], num_new_tokens: List[int], is_generating: bool) -> PagedAttentionCacheData:
+        """Index tensors for the LAST num_new_tokens[i] tokens of every sequence (already allocated with allocate_tokens), in
+        the form fms-extras returns them: slot_mapping / position_ids [B, n] padded with -1 / 0 for ragged counts (the callers
+        flatten with truncate_and_flatten, utils/paged.py:100-108), block_mapping [B, max_blocks], context_lengths [B]."""
+        n_max = max(num_new_tokens) if num_new_tokens else 0
+        B = len(sequence_ids)
+        slots = torch.full((B, n_max), -1, dtype=torch.int64)
+        pos = torch.zeros((B, n_max), dtype=torch.int64)
+        for i, (sid, n) in enumerate(zip(sequence_ids, num_new_tokens)):
+            L = self._lens[sid]
+            p = torch.arange(L - n, L, dtype=torch.int64)
+            blocks = torch.tensor(self._blocks[sid], dtype=torch.int64)
+            slots[i, :n] = blocks[p // self.block_size] * self.block_size + p % self.block_size
+            pos[i, :n] = p
+        lens = [self._lens[s] for s in sequence_ids]
+        return PagedAttentionCacheData(
+            sequence_ids=list(sequence_ids), slot_mapping=slots.to(self.device), block_mapping=self.block_table_tensor(sequence_ids),
+            context_lengths=torch.tensor(lens, dtype=torch.int32, device=self.device), position_ids=pos.to(self.device),
+            max_sequence_length=max(lens) if lens else 0, query_length=n_max, is_generating=is_generating)
 
     def sequence_length(self, sid: int) -> int:
         return self._lens[sid]
@@ -179,3 +274,76 @@ class PagedKVCacheManager:
             pos = torch.arange(st, st + n, dtype=torch.int64)
             out.append(blocks[pos // self.block_size] * self.block_size + pos % self.block_size)
         return torch.cat(out).to(self.device, non_blocking=True) if out else torch.empty(0, dtype=torch.int64, device=self.device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Input preparation of the paged calling convention (the pure index arithmetic of utils/paged.py:82-159, 222-257, 259-326 in the
+# reference; the speculator model itself, fms-extras' MLPSpeculator, is not part of this library).
+# ---------------------------------------------------------------------------------------------------------------------
+def prepare_inputs_for_prefill(num_tokens_per_sequence: List[int], kv_cache_manager: PagedKVCacheManager):
+    """-> (position_ids [T], cache_data in prefill form): new sequences with their prompt tokens allocated (utils/paged.py:139-159)."""
+    sids = kv_cache_manager.allocate_tokens(num_tokens_per_sequence)
+    cd = kv_cache_manager.cache_data(sids, num_tokens_per_sequence, is_generating=False)
+    keep = cd.slot_mapping.reshape(-1) >= 0  # ragged prompts: drop the padding of the [B, n_max] form
+    position_ids = cd.position_ids.reshape(-1)[keep]
+    cd.slot_mapping = cd.slot_mapping.reshape(-1)[keep]
+    lens = torch.tensor([0] + list(num_tokens_per_sequence), dtype=torch.int32, device=cd.context_lengths.device)
+    cd.context_lengths = torch.cumsum(lens, 0, dtype=torch.int32)
+    return position_ids, cd
+
+
+def expand_generation_cache_data(cd: PagedAttentionCacheData):
+    """[B, n] allocation form -> one row per query token: token j of the n new tokens of a sequence of length L attends
+    L - (n - 1 - j) keys over the sequence's blocks (utils/paged.py:109-134, 230-241).  -> (position_ids [B n], cache_data)."""
+    n = cd.query_length
+    B = cd.context_lengths.shape[0]
+    back = torch.arange(n - 1, -1, -1, dtype=torch.int32, device=cd.context_lengths.device)
+    cd.context_lengths = (cd.context_lengths.view(B, 1) - back.view(1, n)).reshape(-1).contiguous()
+    cd.block_mapping = cd.block_mapping.repeat_interleave(n, dim=0).contiguous()
+    cd.slot_mapping = cd.slot_mapping.reshape(-1)
+    return cd.position_ids.reshape(-1), cd
+
+
+def prepare_inputs_without_speculation(parent_sequence_ids: List[int], kv_cache_manager: PagedKVCacheManager):
+    """one more token for every running sequence (utils/paged.py:82-136) -> (position_ids [B], cache_data in generation form)"""
+    kv_cache_manager.allocate_tokens([1] * len(parent_sequence_ids), parent_sequence_ids)
+    return expand_generation_cache_data(kv_cache_manager.cache_data(parent_sequence_ids, [1] * len(parent_sequence_ids), True))
+
+
+def prepare_candidates(parent_sequence_ids: List[int], n_candidates: int, n_tokens: int, kv_cache_manager: PagedKVCacheManager):
+    """speculative step: `n_candidates` child sequences per parent, `n_tokens` (= 1 + speculated) new tokens each
+    (utils/paged.py:185-203).  -> (position_ids [B k n], cache_data in generation form, children per parent)."""
+    children, flat = [], []
+    for parent in parent_sequence_ids:
+        kids = kv_cache_manager.add_child_sequences(parent, n_candidates)
+        children.append(kids)
+        flat.extend(kids)
+    try:
+        kv_cache_manager.allocate_tokens([n_tokens] * len(flat), flat)
+    except BaseException:
+        kv_cache_manager.free_sequences(flat)
+        raise
+    position_ids, cd = expand_generation_cache_data(kv_cache_manager.cache_data(flat, [n_tokens] * len(flat), True))
+    return position_ids, cd, children
+
+
+def accept_candidates(candidate_inputs: torch.Tensor, next_tokens: torch.Tensor, children: List[List[int]],
+                      kv_cache_manager: PagedKVCacheManager):
+    """The acceptance rule of utils/paged.py:279-324.  candidate_inputs [B, k, n]: the tokens fed for each candidate (the last
+    accepted token followed by n - 1 speculated ones); next_tokens [B, k, n]: the model's greedy choice after each of them.
+    A candidate's speculated token j + 1 is correct while it equals the model's choice after token j; the candidate with the
+    longest correct prefix wins, the others are freed, the winner forgets its wrong tail.
+    -> (surviving sequence ids [B], accepted new tokens per parent: the model's choices along the winner's correct prefix)."""
+    B, k, n = candidate_inputs.shape
+    agree = (candidate_inputs.roll(-1, 2) == next_tokens).cumprod(2)
+    n_correct = agree.sum(2).clamp(0, n - 1)           # [B, k]; clamp: a wrap-around match of the rolled last column does not count
+    best = n_correct.argmax(1)
+    survivors, accepted = [], []
+    for b, kids in enumerate(children):
+        w = int(best[b])
+        c = int(n_correct[b, w])
+        kv_cache_manager.free_sequences(kids[:w] + kids[w + 1:])
+        kv_cache_manager.remove_tokens(kids[w], n - c - 1)
+        survivors.append(kids[w])
+        accepted.append(next_tokens[b, w, :c + 1].tolist())
+    return survivors, accepted
