@@ -105,6 +105,39 @@ int b200_embedding(const void* table, const int64_t* ids, void* out, int64_t T, 
  * `scores[idx, eos] = -inf` (utils/tokens.py:244-246) folded into the arg-max. */
 int b200_argmax(const void* logits, int64_t* out_ids, int64_t B, int64_t V, int64_t ld, const int64_t* banned_ids, void* stream);
 
+/* ---- fused next-token chooser ------------------------------------------------------------------------------
+ * One launch per step replaces HeterogeneousNextTokenChooser.__call__ (utils/tokens.py:238-271) for batches without
+ * typical-p: min_new_tokens EOS mask, length penalty, repetition penalty (utils/logits_process.py:93-143), temperature,
+ * top-k, top-p (:146-317), greedy arg-max or seeded sampling per row (tokens.py:30-78), and the chosen token's log-softmax
+ * and rank over the warped scores (tokens.py:388-425).  Per-row arrays are device pointers, NULL = off for every row.
+ * Deterministic (integer / fixed-point accumulation): tensor-parallel shards choose identically.  CUDA-graph capturable:
+ * the sampling draw counters live on the device. */
+typedef struct {
+  const void* logits;      /* fp16 [B, ld] */
+  void* warped_scratch;    /* fp16 [B, V] workspace; holds the warped scores afterwards */
+  int64_t ld, V;           /* V <= 131072 */
+  int32_t B;
+  int32_t history_len_bias;      /* see position_ids */
+  const float* temperature;      /* [B]; 0 = greedy row */
+  const int32_t* top_k;          /* [B]; 0 = off */
+  const float* top_p;            /* [B]; 1 = off */
+  const float* rep_penalty;      /* [B]; 1 = off; needs history + position_ids */
+  const int64_t* history;        /* [B, history_stride] token ids (FlashCausalLMBatch.all_input_ids_tensor) */
+  int64_t history_stride;
+  const int64_t* position_ids;   /* [B]: every row sees history[:, :max(position_ids) + history_len_bias], the reference's
+                                    all_input_ids_tensor[:, :max_seqlen] (flash_causal_lm.py:525-527) */
+  int64_t rep_exclude_id;        /* token exempt from the repetition penalty when B != 1 (pad == eos case, logits_process.py:98-118), or -1 */
+  const int64_t* banned_ids;     /* [B]: id masked to -inf (min_new_tokens, tokens.py:242-246) or -1 */
+  const float* length_penalty_factor; /* [B]: pow(decay, steps past start) - 1 for the EOS score (tokens.py:247-252), 0 = off */
+  int64_t eos_id;
+  const uint64_t* seeds;         /* [B] Philox key of sampling rows */
+  int64_t* counters;             /* [B] draws made so far (advanced by the kernel) */
+  int64_t* next_ids;             /* out [B] */
+  float* logprobs;               /* out [B] or NULL */
+  int32_t* ranks;                /* out [B] or NULL */
+} B200ChooserParams;
+int b200_choose_tokens(const B200ChooserParams* params /* host */, void* stream);
+
 /* ---- decode attention over the paged KV pool ----------------------------------------------------------
  * replaces attention(q, layer_past[:,0], layer_past[:,1], cu_seqlens, max_s, scale, cu_seqlens_q, 1, False)
  * (utils/flash_attn.py:43-127 <- flash_llama_modeling.py:285-295) and fms-extras paged_attention

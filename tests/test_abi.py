@@ -52,7 +52,7 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
     """compile the header with gcc and compare sizeof / offsetof of every struct field with the ctypes mirror"""
     import subprocess
     structs = {"B200Linear": lib.B200Linear, "B200LlamaLayer": lib.B200LlamaLayer, "B200LlamaWeights": lib.B200LlamaWeights,
-               "B200LlamaStep": lib.B200LlamaStep, "B200SplitK": lib.B200SplitK}
+               "B200LlamaStep": lib.B200LlamaStep, "B200SplitK": lib.B200SplitK, "B200ChooserParams": lib.B200ChooserParams}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')

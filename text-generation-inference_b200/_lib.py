@@ -64,6 +64,13 @@ class B200SplitK(ctypes.Structure):
                 ("N", ctypes.c_int32), ("T", ctypes.c_int32)]
 
 
+class B200ChooserParams(ctypes.Structure):
+    _fields_ = [("logits", _P), ("warped_scratch", _P), ("ld", _L), ("V", _L), ("B", ctypes.c_int32), ("history_len_bias", ctypes.c_int32),
+                ("temperature", _P), ("top_k", _P), ("top_p", _P), ("rep_penalty", _P), ("history", _P), ("history_stride", _L),
+                ("position_ids", _P), ("rep_exclude_id", _L), ("banned_ids", _P), ("length_penalty_factor", _P), ("eos_id", _L),
+                ("seeds", _P), ("counters", _P), ("next_ids", _P), ("logprobs", _P), ("ranks", _P)]
+
+
 class B200Linear(ctypes.Structure):
     _fields_ = [("weight", _P), ("qweight", _P), ("perm", _P), ("_unused", _P), ("bias", _P), ("N", _L), ("K", _L),
                 ("groupsize", ctypes.c_int32), ("layout", ctypes.c_int32)]
@@ -95,6 +102,7 @@ class B200LlamaStep(ctypes.Structure):
 
 _WP, _SP, _KP = ctypes.POINTER(B200LlamaWeights), ctypes.POINTER(B200LlamaStep), ctypes.POINTER(B200SplitK)
 SIGNATURES.update({
+    "b200_choose_tokens": (_I, [ctypes.POINTER(B200ChooserParams), _P]),
     "b200_gemm_w4a16_deferred": (_I, [_P, _P, _P, _L, _L, _L, _I, _I, _P, _KP, _P]),
     "b200_gemm_f16_deferred": (_I, [_P, _P, _P, _L, _L, _L, _P, _KP, _P]),
     "b200_splitk_reduce": (_I, [_KP, _P, _P]),

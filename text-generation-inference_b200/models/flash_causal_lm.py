@@ -28,6 +28,7 @@ from .model import Model
 from .types import Batch, GenerateError
 
 USE_CUDA_GRAPHS = __import__("os").getenv("B200_CUDA_GRAPHS", "true").lower() != "false"
+FUSED_CHOOSER = __import__("os").getenv("B200_FUSED_CHOOSER", "1") != "0"
 
 
 @dataclass
@@ -297,21 +298,28 @@ class FlashCausalLM(Model):
 
     # --------------------------------------------------------------------------------------------- fused greedy decode
     def _can_fuse_greedy(self, batch) -> bool:
-        """All-greedy batch with no per-token details on a single rank: arg-max (with the min_new_tokens EOS mask)
-        runs inside the step and the ids chain device-to-device; the host reads back B ids per step."""
+        """The token is chosen on the device inside the (CUDA-graph replayed) step and the ids chain device-to-device; the host
+        reads back B ids (+ log-probabilities / ranks when asked) per step.  Plain greedy batches arg-max inside the C++ step
+        (with the min_new_tokens EOS mask); sampling, penalties, top-k / top-p, logprobs and ranks go through the fused chooser
+        kernel (csrc/chooser.cu).  Typical-p and top-n details stay on the op-by-op path."""
         # families without the C++ step runtime (flash GPT-NeoX) run op by op unless their Python step is switched on
         if not getattr(self.model, "fused_greedy_enabled", hasattr(self.model, "make_step")):
             return False
-        if not batch.next_token_chooser.is_plain_greedy:
+        chooser = batch.next_token_chooser
+        if chooser.is_plain_greedy and not any(r.details.logprobs or r.details.ranks or r.details.top_n_toks for r in batch.requests):
+            return True
+        if not FUSED_CHOOSER or any(r.details.top_n_toks for r in batch.requests):
             return False
-        return not any(r.details.logprobs or r.details.ranks or r.details.top_n_toks for r in batch.requests)
+        tp = getattr(self.engine, "world_size", 1)
+        V = self.model.lm_head.linear.weight.shape[0] * (tp if getattr(self.model.lm_head, "should_gather", False) else 1)
+        return V <= 131072 and all(x >= 1.0 for x in chooser.typical_p) and self.dtype == torch.float16
 
     def _decode_fused_greedy(self, batch):
         kv, B = batch.past_key_values, len(batch)
         chooser = batch.next_token_chooser
         key = (batch.input_ids.data_ptr(), batch.position_ids.data_ptr(), kv.block_table.data_ptr(), kv.context_lens.data_ptr(),
                kv.slot_mapping.data_ptr(), batch.all_input_ids_tensor.data_ptr(), batch.cu_seqlens.data_ptr(), B,
-               self.model.scratch.version)
+               self.model.scratch.version, id(chooser))
         st = getattr(batch, "_fused", None)
         if st is None or st["key"] != key:
             V = self.model.lm_head.linear.weight.shape[0]
@@ -320,7 +328,11 @@ class FlashCausalLM(Model):
                       banned=torch.full((B,), -1, dtype=torch.int64, device=self.device), banned_host=[-1] * B,
                       steps=0, graph=None, max_s_cap=0)
             tp = getattr(self.engine, "world_size", 1)
-            in_step = tp == 1 or getattr(self.model, "greedy_ids_in_step", False)
+            plain = chooser.is_plain_greedy and not any(r.details.logprobs or r.details.ranks for r in batch.requests)
+            st["device_chooser"] = None if plain else chooser.device_chooser()
+            st["want_logprobs"] = any(r.details.logprobs for r in batch.requests)
+            st["want_ranks"] = any(r.details.ranks for r in batch.requests)
+            in_step = plain and (tp == 1 or getattr(self.model, "greedy_ids_in_step", False))
             st["ids_in_step"] = in_step
             st["step"] = self.model.make_step(T=B, B=B, is_prefill=False, max_s=max(batch.total_lengths), input_ids=batch.input_ids,
                                               position_ids=batch.position_ids, kv=kv, logits=st["logits"],
@@ -333,20 +345,33 @@ class FlashCausalLM(Model):
                 st["gathered"] = torch.empty(tp, B, V, dtype=torch.float16, device=self.device)
                 st["full"] = torch.empty(B, tp * V, dtype=torch.float16, device=self.device)
             batch._fused = st
-        # min_new_tokens EOS mask (utils/tokens.py:242-246) as a per-row banned id for the in-step arg-max
-        eos = chooser.eos_token_id
-        banned = [eos if c < m else -1 for c, m in zip(chooser.current_tokens, chooser.min_new_tokens)]
-        for i, bnd in enumerate(banned):
-            if bnd >= 0:
-                chooser.current_tokens[i] += 1
-        if banned != st["banned_host"]:
-            st["banned"].copy_(torch.tensor(banned, dtype=torch.int64), non_blocking=True)
-            st["banned_host"] = banned
+        dc = st["device_chooser"]
+        if dc is None:
+            # min_new_tokens EOS mask (utils/tokens.py:242-246) as a per-row banned id for the in-step arg-max
+            eos = chooser.eos_token_id
+            banned = [eos if c < m else -1 for c, m in zip(chooser.current_tokens, chooser.min_new_tokens)]
+            for i, bnd in enumerate(banned):
+                if bnd >= 0:
+                    chooser.current_tokens[i] += 1
+            if banned != st["banned_host"]:
+                st["banned"].copy_(torch.tensor(banned, dtype=torch.int64), non_blocking=True)
+                st["banned_host"] = banned
+        else:
+            dc.set_step(*chooser.step_masks())  # EOS mask / length-penalty factors of this step; draw counters advance on the device
         start_time = time.time_ns()
         self._run_fused_step(batch, st)
         forward_time_ns = time.time_ns() - start_time
-        ids = st["next_ids"].tolist()  # the step's one D2H read
-        generated = [TokenInfo(request_id=r.id, token_id=tok) for r, tok in zip(batch.requests, ids)]
+        ids = st["next_ids"].tolist()  # the step's D2H read
+        lps = dc.logprobs.tolist() if dc is not None and st["want_logprobs"] else None
+        rks = dc.ranks.tolist() if dc is not None and st["want_ranks"] else None
+        generated = []
+        for i, (r, tok) in enumerate(zip(batch.requests, ids)):
+            info = TokenInfo(request_id=r.id, token_id=tok)
+            if lps is not None and r.details.logprobs:
+                info.logprob = lps[i]
+            if rks is not None and r.details.ranks:
+                info.rank = rks[i]
+            generated.append(info)
         batch.input_lengths = [n + 1 for n in batch.input_lengths]
         st["steps"] += 1
         return generated, [], forward_time_ns
@@ -368,14 +393,20 @@ class FlashCausalLM(Model):
                 kv.block_table.data_ptr(), kv.block_table.stride(0), kv.context_lens.data_ptr(), batch.position_ids.data_ptr(),
                 kv.slot_mapping.data_ptr(), None, None, B, stream), "decode_advance")
             self.model.run_step(s)
-            if getattr(self.engine, "world_size", 1) > 1 and not st.get("ids_in_step", False):
+            if not st.get("ids_in_step", False):
                 from .. import ops
+                logits = st["logits"]
                 if "gathered" in st:
                     torch.distributed.all_gather_into_tensor(st["gathered"], st["logits"], group=self.model.process_group)
                     st["full"].view(B, -1, st["logits"].shape[1]).copy_(st["gathered"].permute(1, 0, 2))
-                    ops.argmax(st["full"], st["banned"], out=st["next_ids"])
+                    logits = st["full"]
+                dc = st.get("device_chooser")
+                if dc is not None:
+                    # position_ids hold the index of each row's INPUT token here: the history is one longer
+                    dc.launch(batch.all_input_ids_tensor, batch.position_ids, logits, st["want_logprobs"], st["want_ranks"],
+                              out_ids=st["next_ids"], history_len_bias=1)
                 else:
-                    ops.argmax(st["logits"], st["banned"], out=st["next_ids"])
+                    ops.argmax(logits, st["banned"], out=st["next_ids"])
             batch.position_ids.add_(1)
             batch.input_ids.copy_(st["next_ids"])
             batch.all_input_ids_tensor.scatter_(dim=1, index=batch.position_ids[:, None], src=st["next_ids"][:, None])
@@ -414,6 +445,28 @@ class FlashCausalLM(Model):
         else:
             logits = out
         chooser = batch.next_token_chooser
+        details = [r.details for r in batch.requests]
+        if (FUSED_CHOOSER and not chooser.is_plain_greedy and chooser.device_eligible(logits)
+                and not any(d.top_n_toks or (prefill and d.input_toks) for d in details)):
+            # one fused kernel instead of the warper chain + log_softmax (csrc/chooser.cu); position_ids already point at the slot
+            # of the token being chosen, i.e. they equal the history length
+            want_lp, want_rk = any(d.logprobs for d in details), any(d.ranks for d in details)
+            next_ids, lps, rks = chooser.choose_on_device(batch.all_input_ids_tensor, batch.position_ids, logits.contiguous(),
+                                                          want_lp, want_rk)
+            next_ids = next_ids.clone()
+            batch.all_input_ids_tensor.scatter_(dim=1, index=batch.position_ids[:, None], src=next_ids[:, None])
+            ids = next_ids.tolist()
+            lps = lps.tolist() if lps is not None else None
+            rks = rks.tolist() if rks is not None else None
+            for i, (r, tok) in enumerate(zip(batch.requests, ids)):
+                info = TokenInfo(request_id=r.id, token_id=tok)
+                if lps is not None and r.details.logprobs:
+                    info.logprob = lps[i]
+                if rks is not None and r.details.ranks:
+                    info.rank = rks[i]
+                generated.append(info)
+                batch.input_lengths[i] += 1
+            return next_ids
         next_ids, scores, logprobs = chooser(input_ids=batch.all_input_ids_tensor[:, :batch.max_seqlen], scores=logits)
         batch.all_input_ids_tensor.scatter_(dim=1, index=batch.position_ids[:, None], src=next_ids[:, None])
         plain = not any(r.details.logprobs or r.details.ranks or r.details.top_n_toks or (prefill and r.details.input_toks)

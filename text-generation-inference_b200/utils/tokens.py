@@ -30,6 +30,8 @@ SINGLE_ZERO, SINGLE_NONE, SINGLE_NAN = [0], [None], [float("nan")]
 class Sampling:
     def __init__(self, seed: Optional[int] = None, device: str = "cpu"):
         self.generator = None if seed is None else torch.Generator(device).manual_seed(seed)
+        self.seed = seed   # the fused device chooser keys its Philox stream with it ...
+        self.draws = 0     # ... and counts the draws made so far (host mirror of the device counter)
 
     def __call__(self, logits):
         probs = torch.nn.functional.softmax(logits, -1)
@@ -103,6 +105,10 @@ class HeterogeneousNextTokenChooser:
         else:
             self.choice = Greedy()
         self.warpers = warpers
+        # per-request parameters as given: the fused device chooser (csrc/chooser.cu) takes them as arrays
+        self.temperature, self.top_k, self.top_p, self.typical_p = list(temperature), list(top_k), list(top_p), list(typical_p)
+        self.repetition_penalty = list(repetition_penalty)
+        self._device = None  # DeviceChooser, built on first use
         self.eos_token_id, self.pad_token_id = eos_token_id, pad_token_id
         self.length_penalty = length_penalty
         self.min_new_tokens = min_new_tokens
@@ -125,6 +131,45 @@ class HeterogeneousNextTokenChooser:
 
     def eos_masked_rows(self) -> List[int]:
         return [i for i, (c, m) in enumerate(zip(self.current_tokens, self.min_new_tokens)) if c < m]
+
+    # ------------------------------------------------------------------------------------------ fused device chooser
+    def device_eligible(self, scores: torch.Tensor) -> bool:
+        """One b200_choose_tokens launch can stand in for __call__: fp16 scores on the GPU, vocabulary within the kernel's bitmap,
+        nobody asks for typical-p (it stays on the torch path) and logits are not forced to fp32."""
+        return (scores.is_cuda and scores.dtype == torch.float16 and scores.dim() == 2 and scores.stride(1) == 1
+                and scores.shape[1] <= 131072 and not FP32_LOGITS and all(x >= 1.0 for x in self.typical_p))
+
+    def step_masks(self) -> Tuple[List[int], List[float]]:
+        """Host bookkeeping of one step, exactly the loop at the top of __call__ (tokens.py:240-252): -> per row the id to mask
+        (EOS while fewer than min_new_tokens were produced, else -1) and the length-penalty factor pow(decay, past) - 1 (else 0)."""
+        banned, factors = [], []
+        for idx, (cur, mn, lp) in enumerate(zip(self.current_tokens, self.min_new_tokens, self.length_penalty)):
+            ban, fac = -1, 0.0
+            if cur < mn:
+                ban = self.eos_token_id
+                self.current_tokens[idx] += 1
+            elif lp is not None:
+                past = cur - lp[0]
+                if past > 0:
+                    fac = pow(lp[1], past) - 1
+                self.current_tokens[idx] += 1
+            banned.append(ban)
+            factors.append(fac)
+        return banned, factors
+
+    def device_chooser(self) -> "DeviceChooser":
+        if self._device is None:
+            self._device = DeviceChooser(self)
+        return self._device
+
+    def choose_on_device(self, all_input_ids: torch.Tensor, position_ids: torch.Tensor, scores: torch.Tensor,
+                         want_logprobs: bool, want_ranks: bool, out_ids: Optional[torch.Tensor] = None):
+        """-> (next_ids [B] int64, logprobs [B] float32 or None, ranks [B] int32 or None), all on the device.
+        all_input_ids / position_ids: the batch's history tensor and the position of each row's input token."""
+        dc = self.device_chooser()
+        banned, factors = self.step_masks()
+        dc.set_step(banned, factors)
+        return dc.launch(all_input_ids, position_ids, scores, want_logprobs, want_ranks, out_ids)
 
     def __call__(self, input_ids: torch.Tensor, scores: torch.Tensor):
         if FP32_LOGITS:
@@ -170,6 +215,10 @@ class HeterogeneousNextTokenChooser:
             current_tokens=current_tokens)
 
     def filter(self, indices):
+        self.temperature, self.top_k, self.top_p = ([lst[i] for i in indices] for lst in (self.temperature, self.top_k, self.top_p))
+        self.typical_p = [self.typical_p[i] for i in indices]
+        self.repetition_penalty = [self.repetition_penalty[i] for i in indices]
+        self._device = None  # rebuilt from the lists (and the Sampling objects' draw counts) on next use
         if self.repetition_processor is not None:
             self.repetition_processor = self.repetition_processor.filter(indices)
         self.warpers = [w for w in (warper.filter(indices) for warper in self.warpers) if w is not None]
@@ -183,6 +232,87 @@ class HeterogeneousNextTokenChooser:
         else:
             self.choice = Greedy()
         return self
+
+
+class DeviceChooser:
+    """Device-side arrays of a HeterogeneousNextTokenChooser for b200_choose_tokens (csrc/chooser.cu): built once per batch
+    composition, the per-step masks are refreshed with two small host-to-device copies, the draw counters live on the device so
+    that the launch can be replayed from a CUDA graph."""
+
+    def __init__(self, chooser: HeterogeneousNextTokenChooser):
+        dev = chooser.device
+        B = len(chooser.do_sample)
+        self.chooser, self.B = chooser, B
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def as_scores_dtype(values):
+            # the torch warpers hold their parameters in the scores' dtype (fp16 1.2 is 1.2002): round the same way
+            return torch.tensor(values, dtype=torch.float16).to(**f32)
+
+        self.temperature = as_scores_dtype([t if s else 0.0 for t, s in zip(chooser.temperature, chooser.do_sample)])
+        self.top_k = torch.tensor([int(k) for k in chooser.top_k], dtype=torch.int32, device=dev) if any(chooser.top_k) else None
+        # logits_process.py:203 keeps `1 - top_p` in the scores' dtype; hand the kernel the p that reproduces that complement
+        self.top_p = (1.0 - (1 - torch.tensor(chooser.top_p, dtype=torch.float16)).to(**f32)) if any(p < 1.0 for p in chooser.top_p) else None
+        self.rep = as_scores_dtype(chooser.repetition_penalty) if any(r != 1.0 for r in chooser.repetition_penalty) else None
+        self.rep_exclude = chooser.eos_token_id if (chooser.eos_token_id is not None and chooser.eos_token_id == chooser.pad_token_id) else -1
+        samplings = chooser.samplings
+        self.sampled_rows = [i for i, smp in enumerate(samplings) if smp is not None]
+        # a request without a seed draws a stream of its own; sharded deployments always send one (router/src/validation.rs:167-177)
+        seeds = [((smp.seed if smp.seed is not None else 0x9E3779B97F4A7C15 ^ id(smp)) & 0x7FFFFFFFFFFFFFFF) if smp is not None else 0
+                 for smp in samplings]
+        self.seeds = torch.tensor(seeds, dtype=torch.int64, device=dev)
+        self.counters = torch.tensor([smp.draws if smp is not None else 0 for smp in samplings], dtype=torch.int64, device=dev)
+        self.banned = torch.full((B,), -1, dtype=torch.int64, device=dev)
+        self.factors = torch.zeros(B, **f32)
+        self._banned_host, self._factors_host = [-1] * B, [0.0] * B
+        self.uses_length_penalty = any(lp is not None for lp in chooser.length_penalty)
+        self.next_ids = torch.empty(B, dtype=torch.int64, device=dev)
+        self.logprobs = torch.empty(B, **f32)
+        self.ranks = torch.empty(B, dtype=torch.int32, device=dev)
+        self.scratch = None
+
+    def set_step(self, banned: List[int], factors: List[float]) -> None:
+        if banned != self._banned_host:
+            self.banned.copy_(torch.tensor(banned, dtype=torch.int64), non_blocking=True)
+            self._banned_host = banned
+        if factors != self._factors_host:
+            self.factors.copy_(torch.tensor(factors, dtype=torch.float32), non_blocking=True)
+            self._factors_host = factors
+        for i in self.sampled_rows:  # host mirror of the device draw counters
+            self.chooser.samplings[i].draws += 1
+
+    def launch(self, all_input_ids, position_ids, scores, want_logprobs: bool, want_ranks: bool, out_ids=None,
+               history_len_bias: int = 0):
+        """history_len_bias: every row's history is all_input_ids[:, :max(position_ids) + bias] (the reference's
+        `all_input_ids_tensor[:, :max_seqlen]`): 0 when position_ids already point at the slot of the token being chosen
+        (after a prefill / op-by-op decode), 1 inside the fused step, where they still index the input token."""
+        import ctypes
+
+        from .. import _lib
+        B, V = scores.shape
+        assert B == self.B
+        if self.scratch is None or self.scratch.shape != (B, V):
+            self.scratch = torch.empty(B, V, dtype=torch.float16, device=scores.device)
+        ids = out_ids if out_ids is not None else self.next_ids
+        p = _lib.B200ChooserParams()
+        p.logits, p.warped_scratch, p.ld, p.V, p.B = scores.data_ptr(), self.scratch.data_ptr(), scores.stride(0), V, B
+        p.history_len_bias = history_len_bias
+        p.temperature = self.temperature.data_ptr()
+        p.top_k = self.top_k.data_ptr() if self.top_k is not None else None
+        p.top_p = self.top_p.data_ptr() if self.top_p is not None else None
+        if self.rep is not None:
+            p.rep_penalty, p.history, p.history_stride = self.rep.data_ptr(), all_input_ids.data_ptr(), all_input_ids.stride(0)
+            p.position_ids = position_ids.data_ptr()
+        p.rep_exclude_id = self.rep_exclude
+        p.banned_ids = self.banned.data_ptr()
+        p.length_penalty_factor = self.factors.data_ptr() if self.uses_length_penalty else None
+        p.eos_id = self.chooser.eos_token_id if self.chooser.eos_token_id is not None else -1
+        p.seeds, p.counters = self.seeds.data_ptr(), self.counters.data_ptr()
+        p.next_ids = ids.data_ptr()
+        p.logprobs = self.logprobs.data_ptr() if want_logprobs else None
+        p.ranks = self.ranks.data_ptr() if want_ranks else None
+        _lib.check(_lib.load().b200_choose_tokens(ctypes.byref(p), torch.cuda.current_stream().cuda_stream), "choose_tokens")
+        return ids, (self.logprobs if want_logprobs else None), (self.ranks if want_ranks else None)
 
 
 def get_token_info(request, scores: torch.Tensor, next_token: torch.Tensor, logprobs: Optional[torch.Tensor]) -> TokenInfo:
