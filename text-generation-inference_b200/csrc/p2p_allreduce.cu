@@ -1,12 +1,11 @@
 // One-shot all-reduce over NVLink peer memory for the tensor-parallel layer boundary.
 //
-// Replaces (when enabled, B200_P2P_ALLREDUCE=1): torch.distributed.all_reduce after the row-parallel o_proj / down_proj and the
+// Replaces (default for decode-sized messages; B200_P2P_ALLREDUCE=0 keeps NCCL): torch.distributed.all_reduce after the row-parallel o_proj / down_proj and the
 // vocab-parallel embedding (/root/reference/server/text_generation_server/utils/layers.py:303-306 TensorParallelRowLinear,
 // :343-345 TensorParallelEmbedding; flash_llama_modeling.py:296, :335) for the decode-sized messages of the step
 // (bs 64 x hidden 4096 fp16 = 512 KB): NCCL costs 10-15 us per call there, twice per layer.
 //
-// EXPERIMENTAL: written without multi-GPU time left in the round, off by default, NCCL stays the product path until
-// tests/test_gpu_experimental.py has passed on a 2-GPU box.
+// Validated on a 2-GPU B200 box in round 2 (tests/test_gpu_p2p.py, tests/test_gpu_tp.py; profiles/r2_tp2_and_splitk_validation.txt).
 //
 // Design.  Every rank owns a *window* in its own HBM, allocated here with cudaMalloc and exported over CUDA IPC:
 //     [kBlocks][kMaxWorld] u32 arrival flags | [kBlocks] u32 epochs | pad to 4 KB | 2 slots x max_bytes of fp16 data

@@ -3,7 +3,7 @@ process group, opens the safetensors shards with the TP slicing rules and builds
 
 Mirrors /root/reference/server/text_generation_server/inference_engine/engine.py:11-37 (`BaseInferenceEngine`:
 config/tokenizer loading, RANK / WORLD_SIZE, device = rank % device_count) and inference_engine/tgis_native.py:24-139.
-Only the flash decoder families of the hot path exist here (llama, gpt_neox, and - experimental - gpt_bigcode and falcon / RefinedWeb); other model
+Only the flash decoder families of the hot path exist here (llama, gpt_neox, gpt_bigcode and falcon / RefinedWeb); other model
 types raise NotImplementedError.
 """
 from __future__ import annotations

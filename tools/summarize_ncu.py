@@ -36,11 +36,14 @@ for n, v, _, _ in step:
     agg[k][0] += 1
     agg[k][1] += v
 lines = [f"decode step of {workload} (2 layers + head), total {tot / 1e3:.1f} us, {len(step)} launches", ""]
+tag_note = f"profiles/{tag}"
 for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
     lines.append(f"{k:45s} n={c:3d} total={v / 1e3:8.1f} us  avg={v / c / 1e3:7.1f} us  share={v / tot * 100:5.1f}%")
 
 # ---- full report: headline metrics per captured kernel
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# `rep` is the .ncu-rep, or the CSV of its raw page produced on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x_raw.csv`: the
+# reports themselves are too large to bring back)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(raw.splitlines()))
 hdr, units, data = r[0], r[1], r[2:]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
