@@ -152,10 +152,11 @@ def test_generate_token_samples_inside_the_graph_and_matches_the_op_by_op_path(t
             batch, errs = model.batch_type.from_pb(batch_pb(), tok, torch.float16, model.device, None, None, True)
             assert not errs
             res = model.generate_token(batch, first=True)
-            for _ in range(n_new):
+            for step in range(n_new):
                 for t in res[0]:
                     out[t.request_id].append((t.token_id, round(t.logprob, 3) if t.logprob else 0.0, t.rank))
-                res = model.generate_token(batch)
+                if step + 1 < n_new:  # the requests asked for n_new tokens: their rows of the history tensor end there
+                    res = model.generate_token(batch)
         model.kv_cache_manager.free_sequences(batch.sequence_ids)
         return out
 

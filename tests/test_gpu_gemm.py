@@ -102,7 +102,9 @@ def test_gptq_pack_layout(ops):
 
 
 W4_SHAPES = [(64, 4096, 4096, 128), (1, 256, 128, 128), (7, 384, 256, 64), (16, 128, 64, 32), (33, 2560, 2048, 128),
-             (64, 4096, 11008, 128), (128, 512, 1024, 128), (300, 768, 512, -1)]
+             (64, 4096, 11008, 128), (128, 512, 1024, 128), (300, 768, 512, -1),
+             # prefill sizes: persistent CTAs over (token tile, super-tile) items - fewer items than SMs, and several items per CTA
+             (2100, 1280, 1024, 128), (4096, 2048, 512, 64), (5000, 4096, 256, 128)]
 
 
 @pytest.mark.parametrize("T,N,K,gs", W4_SHAPES)

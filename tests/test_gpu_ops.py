@@ -87,9 +87,10 @@ def test_embedding_and_argmax(ops):
 
 
 @pytest.mark.parametrize("h,kv,d", [(8, 8, 128), (32, 4, 64), (8, 2, 128)])
-def test_rope_kv_write_paged(ops, h, kv, d):
+@pytest.mark.parametrize("T", [37, 700])  # 700: the vectorised prefill-sized form (T >= 256)
+def test_rope_kv_write_paged(ops, h, kv, d, T):
     g = torch.Generator().manual_seed(h * d)
-    T, nblocks = 37, 12
+    nblocks = (T + 15) // 16 + 9
     qkv = torch.randn(T, (h + 2 * kv) * d, generator=g).half()
     pos = torch.randint(0, 300, (T,), generator=g)
     cos_t, sin_t = oll.rope_tables(d, 10000.0, 300)

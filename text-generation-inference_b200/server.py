@@ -58,10 +58,18 @@ def memory_scaling_model(model) -> "generate_pb2.MemoryScalingModel":
     cost of a token is its KV bytes; the limit is the pool size.  The router multiplies (router/src/batch_types.rs:68-83)."""
     mgr = model.kv_cache_manager
     per_token = mgr.block_bytes() / mgr.block_size
+    # The router books a request at input + max_new tokens (FlashBatch.batch_max_weight, router/src/batch_types.rs:68-83), which is
+    # what generate_token(first=True) reserves - in whole 16-token blocks per sequence.  The router's model has no per-sequence term,
+    # so the up-to-15 slots a sequence's last block wastes come off the limit instead, for as many sequences as a batch may hold
+    # (the launcher's --max-batch-size is not visible to the shard: 256, overridable with MAX_BATCH_SIZE).
+    max_batch = int(os.getenv("MAX_BATCH_SIZE", "256"))
+    usable_tokens = mgr.total_num_gpu_blocks * mgr.block_size - (mgr.block_size - 1) * max_batch
+    if usable_tokens <= 0:  # a pool too small for the margin: advertise what there is
+        usable_tokens = mgr.total_num_gpu_blocks * mgr.block_size
     return generate_pb2.MemoryScalingModel(
         prefill_linear_coef0=per_token, prefill_quadratic_coef0=0.0, prefill_quadratic_coef1=0.0,
         nexttoken_linear_coef0=0.0, nexttoken_linear_coef1=per_token,
-        weight_limit=int(mgr.total_num_gpu_blocks * mgr.block_bytes()))
+        weight_limit=int(usable_tokens * per_token))
 
 
 class TextGenerationService:
