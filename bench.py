@@ -455,9 +455,17 @@ def run_mixed(args, workload):
     if world > 1:
         dist.barrier()
     sampler.mark()
+    def agree(dt):
+        """every rank advances the session clock by the slowest rank's time: identical admission decisions on all shards"""
+        if world == 1:
+            return dt
+        t = torch.tensor([dt], dtype=torch.float64, device=model.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     with torch.inference_mode():
         out = router_sim.run_session(service, pb, requests, max_bs, lambda p: "test " * len(p), max_batch_tokens=budget, sync=sync,
-                                     on_decode_step=on_step)
+                                     on_decode_step=on_step, agree=agree)
     clocks = sampler.stop()
     st = out["stats"]
     launches = lib.b200_launch_count() - l0

@@ -51,9 +51,13 @@ class _Ctx:
 
 def run_session(service, pb, requests: List[SimRequest], max_batch_size: int, text_of: Callable[[List[int]], str],
                 max_batch_tokens: Optional[int] = None, sync: Optional[Callable[[], None]] = None,
-                on_decode_step: Optional[Callable[[int, int], None]] = None) -> Dict:
+                on_decode_step: Optional[Callable[[int, int], None]] = None,
+                agree: Optional[Callable[[float], float]] = None) -> Dict:
     """max_batch_tokens: admission budget in tokens (prompt + max_new summed over the running requests), the role of the
-    router's weight limit (queue.rs:266-345).  on_decode_step(batch_size, sum of contexts) lets the caller count bytes."""
+    router's weight limit (queue.rs:266-345).  on_decode_step(batch_size, sum of contexts) lets the caller count bytes.
+    agree(seconds) -> seconds: with several shards every rank runs this loop itself (the real router broadcasts each RPC to all
+    shards, sharded_client.rs:38-48); admission depends on the clock, so the ranks must advance it by the SAME amount - pass a
+    max-over-ranks reduction."""
     ctx = _Ctx()
     loop = asyncio.new_event_loop()
     waiting = sorted(requests, key=lambda r: r.arrival_s)
@@ -72,7 +76,8 @@ def run_session(service, pb, requests: List[SimRequest], max_batch_size: int, te
         res = loop.run_until_complete(coro)
         if sync:
             sync()
-        return res, time.perf_counter() - t0
+        dt = time.perf_counter() - t0
+        return res, (agree(dt) if agree else dt)
 
     def n_running():
         return sum(len(v) for v in running.values())
