@@ -51,6 +51,7 @@ WORKLOADS = {
     "llama3-8b-gptq": ("llama-3-8b", "gptq", 64, 1024, 2048),
     "llama2-7b-gptq": ("llama-2-7b", "gptq", 64, 1024, 2048),
     "llama2-7b-fp16": ("llama-2-7b", None, 64, 1024, 2048),
+    "llama3-70b-gptq": ("llama-3-70b", "gptq", 128, 512, 1024),  # steady-state sibling of config[4]; needs --gpus 2 or more
     "tinyllama-fp16": ("tinyllama-1.1b", None, 32, 512, 1024),
     "tiny-test": ("tiny-test", None, 4, 32, 256),
 }

@@ -3,6 +3,7 @@ launch).  The stamps serialise the stream, so PDL overlap between kernels is los
 kernel including its launch gap, warm L2 state as in the served step", and compare its sum with the untraced step time.
 
   python tools/step_trace.py [--workload llama3-8b-gptq] [--context 1536] [--layers N] [--out gpurun_out/step_trace.txt]
+  torchrun --nproc-per-node 8 ... tools/step_trace.py ...   (tensor parallel: the launch list of rank 0's step)
 """
 import argparse
 import collections
@@ -19,15 +20,18 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="llama3-8b-gptq")
-    ap.add_argument("--context", type=int, default=1536)
+    ap.add_argument("--context", type=int, default=None, help="default: the middle of the workload's trajectory")
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     arch, quantize, B, L0, L1 = bench.WORKLOADS[a.workload]
-    model, cfg = bench.build_model(a.workload, 1, 0, a.layers)
+    world, rank = int(os.getenv("WORLD_SIZE", "1")), int(os.getenv("RANK", "0"))  # under torchrun: every rank traces, rank 0 reports
+    model, cfg = bench.build_model(a.workload, world, rank, a.layers)
     from tgis_b200 import _lib
     lib = _lib.load()
     dev = model.device
+    if a.context is None:
+        a.context = (L0 + L1) // 2
     L0 = min(L0, a.context - 8)
     batch, errs = model.batch_type.from_pb(bench.make_batch_pb(B, L0, L1 - L0), model.tokenizer, model.dtype, dev, None, None, True)
     lines = []
@@ -74,7 +78,7 @@ def main():
         t = buf[:n].cpu().tolist()
         dt = [(names[i].split("<")[0].replace("b200::", ""), (t[i] - t[i - 1]) / 1e3) for i in range(1, n)]
         total = (t[n - 1] - t[0]) / 1e3
-        lines.append(f"workload {a.workload} context {cur} layers {cfg.num_hidden_layers}: untraced graph step {untraced_us:.1f} us, "
+        lines.append(f"workload {a.workload} tp{world} context {cur} layers {cfg.num_hidden_layers}: untraced graph step {untraced_us:.1f} us, "
                      f"traced (serialised) step {total:.1f} us, {n - 1} launches")
         agg = collections.OrderedDict()
         for k, v in dt:
@@ -88,6 +92,8 @@ def main():
         for i, (k, v) in enumerate(dt[:3 * per_layer]):
             lines.append(f"     {i:3d} {k:40s} {v:8.2f} us")
     text = "\n".join(lines)
+    if rank != 0:
+        return
     print(text)
     if a.out:
         with open(a.out, "w") as f:
