@@ -136,36 +136,84 @@ p2p_allreduce_f16_kernel(unsigned char* const* __restrict__ peers, __half* __res
 // Replaces, per half-layer of the sharded Llama graph, three things of the reference: the row-parallel linear's
 // torch.distributed.all_reduce (utils/layers.py:318-322), and the fused residual + RMSNorm that consumes its result
 // (flash_llama_modeling.py:132-148) - and, when the row-parallel GEMM ran with deferred split-K reduction, the GEMM's own
-// cross-CTA fix-up as well: the rank-partial row is summed from the fp32 partials straight into the NVLink window.
-// One block per token row t:
-//   1. local rank-partial row (fp16 input, or sum of split-K partials rounded to fp16) -> local window, slot = epoch & 1
-//   2. system-scope fence, then the row's flag in every peer's window <- epoch (st.release.sys over NVLink)
-//   3. wait for every peer's flag for this row (ld.acquire.sys, bounded)
-//   4. read the row from every rank's window in rank order, fp32 accumulation, ONE rounding to fp16 = the all-reduced
-//      hidden state (bit-identical on every rank); x = that + residual (fp32) -> residual_out; RMSNorm -> normed_out
-// Same two-slot / per-index epoch protocol as the chunked kernel above (a row only races with itself), graph-replayable.
+// cross-CTA fix-up as well: the rank-partial row is summed from the fp32 partials straight into an NVLink window.
+//
+// Nothing downstream ever reads the all-reduced hidden state itself, only norm(hidden + residual) and the new residual, and
+// the residual stream is only ever read by the next boundary.  So the exchange is a reduce-scatter by TOKEN ROW followed by a
+// broadcast of the NORMED row: row t belongs to rank t % world, which alone keeps the residual stream of that row.
+// One block per row t, on every rank:
+//   1. this rank's partial row (fp16 input, or sum of split-K partials rounded to fp16) -> stored straight into the OWNER's
+//      window (inbox 1: [slot][t / world][source rank][H]), 16-byte stores over NVLink, no flag and no fence
+//   2. owner block: poll inbox 1 until the row of every source rank has landed, add in rank order with fp32 accumulation, ONE
+//      rounding to fp16 = the all-reduced hidden state; x = that + residual (fp32) -> residual_out[t]; RMSNorm(x) -> normed[t]
+//      locally and stored into every peer's window (inbox 2: [slot][t][H])
+//      other blocks: poll inbox 2 until the normed row landed, copy it to normed[t]
+// "Landed" is read off the data itself (the Lamport trick): an inbox cell holds fp16 -0.0 in every element until written,
+// senders write +0.0 for -0.0, and a receiver re-reads a 16-byte vector until none of its 8 elements is -0.0 - one NVLink
+// one-way latency per hop instead of store / fence / flag / load round trips, and 1.75x the message per rank on the wire
+// instead of 7x (world = 8).  Three slots per row, slot = calls % 3: a block clears the slot of the PREVIOUS call of its row
+// (read only by itself, in an earlier kernel of the stream) for the call after the next; a peer can only write that slot again
+// after it completed the next call, which needs this rank's push of the next call, which is stream-ordered after this
+// kernel.  The per-row call counter lives in the window header and is advanced by the kernel: CUDA-graph replayable.
+// Every rank computes nothing twice and every rank ends with bit-identical normed rows (they are copies).
+// residual / residual_out are only read / written for the rows this rank owns.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kP2PUnwritten = 0x80008000u;  // two fp16 -0.0
+
+__device__ __forceinline__ void st_peer_v4(void* p, const uint4& v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t no_neg_zero(uint32_t w) { return w ^ (__vcmpeq2(w, kP2PUnwritten) & kP2PUnwritten); }
+__device__ __forceinline__ uint4 no_neg_zero(uint4 v) {
+  v.x = no_neg_zero(v.x);
+  v.y = no_neg_zero(v.y);
+  v.z = no_neg_zero(v.z);
+  v.w = no_neg_zero(v.w);
+  return v;
+}
+__device__ __forceinline__ bool landed(const uint4& v) {
+  return (__vcmpeq2(v.x, kP2PUnwritten) | __vcmpeq2(v.y, kP2PUnwritten) | __vcmpeq2(v.z, kP2PUnwritten) | __vcmpeq2(v.w, kP2PUnwritten)) == 0;
+}
+__device__ __forceinline__ uint4 poll_v4(const void* p, unsigned long long t0) {
+  uint4 v = ld_peer_v4(p);
+  while (!landed(v)) {
+    if (global_timer_ns() - t0 > kP2PSpinNs) __trap();
+    v = ld_peer_v4(p);
+  }
+  return v;
+}
+
+// inbox 1 holds ceil(256 / world) owned rows x world sources <= 256 + 7 rows; both inboxes are laid out for h_cap elements per row
+__host__ __device__ inline int64_t p2p_inbox1_rows(int world) { return (int64_t)((kP2PMaxRows + world - 1) / world) * world; }
+
 template <bool kSplitK>
-__global__ void __launch_bounds__(kP2PThreads, 1)
+__global__ void __launch_bounds__(kP2PThreads, 2)
 p2p_allreduce_rmsnorm_kernel(unsigned char* const* __restrict__ peers, const __half* __restrict__ h, const B200SplitK parts,
                              const __half* __restrict__ residual, const __half* __restrict__ gamma, __half* __restrict__ normed,
-                             __half* __restrict__ res_out, int H, float eps, int world, int rank, int64_t slot_bytes) {
+                             __half* __restrict__ res_out, int H, int h_cap, float eps, int world, int rank) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of the row after the residual add
+  float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of the row after the residual add (owner blocks)
   __shared__ float red[32];
-  __shared__ uint32_t s_epoch;
+  __shared__ uint32_t s_calls;
   pdl_launch_dependents();
   const int row = blockIdx.x;
+  const int owner = row % world, own_idx = row / world;
   unsigned char* mine = peers[rank];
-  uint32_t* my_flags = reinterpret_cast<uint32_t*>(mine) + row * kP2PMaxWorld;
-  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(mine) + kP2PMaxRows * kP2PMaxWorld + row;
-  pdl_wait();  // the input is the previous kernel's output; the epoch was written by the previous fused launch of the stream
-  if (threadIdx.x == 0) s_epoch = *my_epoch + 1;
+  uint32_t* my_calls = reinterpret_cast<uint32_t*>(mine) + kP2PMaxRows * kP2PMaxWorld + row;
+  pdl_wait();  // the input is the previous kernel's output; the counter was written by the previous fused launch of the stream
+  if (threadIdx.x == 0) s_calls = *my_calls;
   __syncthreads();
-  const uint32_t epoch = s_epoch;
-  const int64_t row_off = kP2PHeaderBytes + (int64_t)(epoch & 1) * slot_bytes + (int64_t)row * H * 2;
+  const uint32_t calls = s_calls;
+  const int slot = (int)(calls % 3u), prev = (int)((calls + 2u) % 3u);
+  const int64_t row_bytes = (int64_t)h_cap * 2;
+  const int64_t in1_rows = p2p_inbox1_rows(world);
+  const int64_t in2_base = kP2PHeaderBytes + 3 * in1_rows * row_bytes;
+  auto inbox1 = [&](int sl, int src) { return kP2PHeaderBytes + ((int64_t)sl * in1_rows + (int64_t)own_idx * world + src) * row_bytes; };
+  auto inbox2 = [&](int sl) { return in2_base + ((int64_t)sl * kP2PMaxRows + row) * row_bytes; };
+  const uint4 blank = make_uint4(kP2PUnwritten, kP2PUnwritten, kP2PUnwritten, kP2PUnwritten);
 
-  // 1. rank-partial row -> local window
+  // 1. this rank's partial row -> the owner's inbox 1
+  unsigned char* to_owner = peers[owner] + inbox1(slot, rank);
   for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
     uint4 v;
     if constexpr (kSplitK) {
@@ -177,31 +225,35 @@ p2p_allreduce_rmsnorm_kernel(unsigned char* const* __restrict__ peers, const __h
     } else {
       v = *reinterpret_cast<const uint4*>(h + (size_t)row * H + i);
     }
-    *reinterpret_cast<uint4*>(mine + row_off + (int64_t)i * 2) = v;
+    st_peer_v4(to_owner + (int64_t)i * 2, no_neg_zero(v));
   }
-  __threadfence_system();
-  __syncthreads();
-  // 2. tell every peer, 3. wait for every peer
-  if (threadIdx.x < world && threadIdx.x != rank) {
-    uint32_t* theirs = reinterpret_cast<uint32_t*>(peers[threadIdx.x]) + row * kP2PMaxWorld + rank;
-    st_release_sys(theirs, epoch);
-    const unsigned long long t0 = global_timer_ns();
-    while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - epoch) < 0) {
-      if (global_timer_ns() - t0 > kP2PSpinNs) __trap();
-    }
+  const unsigned long long t0 = global_timer_ns();
+
+  if (rank != owner) {
+    // clear the slot of this row's previous call while the owner works, then wait for the normed row
+    unsigned char* old = mine + inbox2(prev);
+    for (int i = threadIdx.x * 8; i < h_cap; i += kP2PThreads * 8) *reinterpret_cast<uint4*>(old + (int64_t)i * 2) = blank;
+    const unsigned char* in = mine + inbox2(slot);
+    for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8)
+      *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = poll_v4(in + (int64_t)i * 2, t0);
+    if (threadIdx.x == 0) *my_calls = calls + 1;
+    return;
   }
-  __syncthreads();
-  // 4. sum in rank order, residual add, statistics
+
+  // 2. owner: sum in rank order, residual add, statistics
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint4 ld[kP2PMaxWorld];
 #pragma unroll
     for (int r = 0; r < kP2PMaxWorld; ++r)
-      if (r < world) ld[r] = ld_peer_v4(peers[r] + row_off + (int64_t)i * 2);  // all peer loads in flight together
+      if (r < world) ld[r] = ld_peer_v4(mine + inbox1(slot, r) + (int64_t)i * 2);  // all sources in flight together
 #pragma unroll
     for (int r = 0; r < kP2PMaxWorld; ++r)
-      if (r < world) add_h8(acc, ld[r]);
+      if (r < world) {
+        if (!landed(ld[r])) ld[r] = poll_v4(mine + inbox1(slot, r) + (int64_t)i * 2, t0);
+        add_h8(acc, ld[r]);
+      }
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = __half2float(__float2half_rn(acc[j]));  // the all-reduce result is an fp16 tensor
@@ -239,6 +291,7 @@ p2p_allreduce_rmsnorm_kernel(unsigned char* const* __restrict__ peers, const __h
   }
   __syncthreads();
   const float rstd = rsqrtf(red[0] / (float)H + eps);
+  const int64_t out_off = inbox2(slot);
   for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
     const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
     const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
@@ -249,9 +302,24 @@ p2p_allreduce_rmsnorm_kernel(unsigned char* const* __restrict__ peers, const __h
       const float2 g = __half22float2(g2[j]);
       o2[j] = __floats2half2_rn(xs[i + 2 * j] * rstd * g.x, xs[i + 2 * j + 1] * rstd * g.y);
     }
+    ov = no_neg_zero(ov);
+    for (int r = 1; r < world; ++r) {  // peers first, starting with the next rank: the ranks' pushes spread over the links
+      const int dst = rank + r < world ? rank + r : rank + r - world;
+      st_peer_v4(peers[dst] + out_off + (int64_t)i * 2, ov);
+    }
     *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = ov;
   }
-  if (threadIdx.x == 0) *my_epoch = epoch;
+  // clear inbox 1 of this row's previous call (all sources)
+  for (int r = 0; r < world; ++r) {
+    unsigned char* old = mine + inbox1(prev, r);
+    for (int i = threadIdx.x * 8; i < h_cap; i += kP2PThreads * 8) *reinterpret_cast<uint4*>(old + (int64_t)i * 2) = blank;
+  }
+  if (threadIdx.x == 0) *my_calls = calls + 1;
+}
+
+__global__ void p2p_fill_kernel(uint4* p, int64_t n, uint32_t word) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = make_uint4(word, word, word, word);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -369,10 +437,16 @@ extern "C" int b200_p2p_create(int64_t max_bytes, int world, int rank, void** ct
   ctx->world = world;
   ctx->rank = rank;
   ctx->max_bytes = (max_bytes + kP2PChunkBytes - 1) / kP2PChunkBytes * kP2PChunkBytes;
-  const size_t bytes = kP2PHeaderBytes + 2 * (size_t)ctx->max_bytes;
+  // the chunked all-reduce and the arg-max use two slots of max_bytes; the fused boundary uses 3 slots x (inbox 1 + inbox 2),
+  // each 256 (+ up to 7) rows of max_bytes / 256, and wants every data cell to read "unwritten" (fp16 -0.0) before its first call
+  const size_t bytes = kP2PHeaderBytes + 7 * (size_t)ctx->max_bytes;
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaMalloc(&ctx->window, bytes);
-  if (e == cudaSuccess) e = cudaMemset(ctx->window, 0, bytes);
+  if (e == cudaSuccess) e = cudaMemset(ctx->window, 0, kP2PHeaderBytes);
+  if (e == cudaSuccess) {
+    p2p_fill_kernel<<<256, 256>>>(reinterpret_cast<uint4*>(ctx->window + kP2PHeaderBytes), (int64_t)(bytes - kP2PHeaderBytes) / 16, kP2PUnwritten);
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess) e = cudaMalloc(&ctx->peer_table, sizeof(unsigned char*) * kP2PMaxWorld);
   if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ctx->window);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -434,7 +508,9 @@ extern "C" int b200_p2p_allreduce_f16(void* ctx_, void* data, int64_t n, void* s
 
 // Fused layer boundary (see the kernel).  Exactly one of h (fp16 [T, H], this rank's partial sums) and h_parts (a deferred
 // row-parallel GEMM, H = h_parts->N, T = h_parts->T) is given.  residual may be NULL (first layer): residual_out then receives
-// the reduced hidden state.  T <= 256, T * H * 2 <= max_bytes, H % 8 == 0, H <= 16384.
+// the reduced hidden state.  residual / residual_out are read / written ONLY for the rows this rank owns (t % world == rank):
+// the residual stream of a row lives on its owner, every rank gets every normed row.  All boundaries of a step must go through
+// this call for that to hold.  T <= 256, 256 * H * 2 <= max_bytes, H % 8 == 0, H <= 16384.
 extern "C" int b200_p2p_allreduce_rmsnorm(void* ctx_, const void* h, const B200SplitK* h_parts, const void* residual, const void* gamma,
                                           void* normed_out, void* residual_out, int64_t T, int64_t H, float eps, void* stream) {
   P2PContext* ctx = (P2PContext*)ctx_;
@@ -451,8 +527,10 @@ extern "C" int b200_p2p_allreduce_rmsnorm(void* ctx_, const void* h, const B200S
     H = h_parts->N;
   }
   if (T == 0) return B200_OK;
-  if (T > kP2PMaxRows || H % 8 != 0 || H > 16384 || T * H * 2 > ctx->max_bytes || (h && ((uintptr_t)h & 15) != 0)) {
-    b200_set_last_error("p2p_allreduce_rmsnorm: need T <= 256, H % 8 == 0, H <= 16384, T * H * 2 <= max_bytes, 16-byte aligned h");
+  // the window is laid out for rows of h_cap elements: 3 x (256 + 7) + 3 x 256 rows fit in the 7 * max_bytes behind the header
+  const int64_t h_cap = ctx->max_bytes / (2 * kP2PMaxRows) / 8 * 8;
+  if (T > kP2PMaxRows || H % 8 != 0 || H > 16384 || H > h_cap || (h && ((uintptr_t)h & 15) != 0)) {
+    b200_set_last_error("p2p_allreduce_rmsnorm: need T <= 256, H % 8 == 0, H <= 16384, 256 * H * 2 <= max_bytes, 16-byte aligned h");
     return B200_ERR_ARG;
   }
   for (int r = 0; r < ctx->world; ++r)
@@ -466,13 +544,13 @@ extern "C" int b200_p2p_allreduce_rmsnorm(void* ctx_, const void* h, const B200S
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel<splitk>", kernel, dim3((unsigned)T), dim3(kP2PThreads), smem, st,
                    (unsigned char* const*)ctx->peer_table, (const __half*)nullptr, *h_parts, (const __half*)residual, (const __half*)gamma,
-                   (__half*)normed_out, (__half*)residual_out, (int)H, eps, ctx->world, ctx->rank, ctx->max_bytes);
+                   (__half*)normed_out, (__half*)residual_out, (int)H, (int)h_cap, eps, ctx->world, ctx->rank);
   } else {
     constexpr auto kernel = p2p_allreduce_rmsnorm_kernel<false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel", kernel, dim3((unsigned)T), dim3(kP2PThreads), smem, st,
                    (unsigned char* const*)ctx->peer_table, (const __half*)h, B200SplitK{}, (const __half*)residual, (const __half*)gamma,
-                   (__half*)normed_out, (__half*)residual_out, (int)H, eps, ctx->world, ctx->rank, ctx->max_bytes);
+                   (__half*)normed_out, (__half*)residual_out, (int)H, (int)h_cap, eps, ctx->world, ctx->rank);
   }
   b200_count_launches(1);
   return B200_OK;
