@@ -273,7 +273,10 @@ void b200_p2p_destroy(void* ctx);
 /* A window serves ONE of the three kernels (allreduce_f16 / allreduce_rmsnorm / argmax): their bookkeeping is per block index.
  * Fused layer boundary: all-reduce of this rank's partial hidden state (h fp16 [T, H], or h_parts = a deferred row-parallel GEMM)
  * + residual add + RMSNorm (utils/layers.py:318-322 followed by flash_llama_modeling.py:132-148).  residual NULL (first layer):
- * residual_out = the reduced hidden state.  T <= 256, T * H * 2 <= max_bytes. */
+ * residual_out = the reduced hidden state.  Row t belongs to rank t % world: every rank receives every row of normed_out, but
+ * residual is read and residual_out written only for the rows the rank owns (the residual stream of a row lives on its owner;
+ * route every boundary of a step through this call).  T <= 2048; the window must have been created with
+ * max_bytes >= 2048 * H * 2. */
 int b200_p2p_allreduce_rmsnorm(void* ctx, const void* h, const B200SplitK* h_parts, const void* residual, const void* gamma,
                                void* normed_out, void* residual_out, int64_t T, int64_t H, float eps, void* stream);
 /* greedy ids of a vocabulary-sharded head without gathering logits (replaces utils/layers.py:249-269 + utils/tokens.py:44-46 for

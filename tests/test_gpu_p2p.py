@@ -140,7 +140,7 @@ def _boundary_worker(rank, world, port, q):
             return normed, red
         return ops.rmsnorm_residual(red, res, gamma, 1e-5)
 
-    for it, T in enumerate([64, 1, 7, 128, 256, 64, 64, 3, 64, 200, 64]):
+    for it, T in enumerate([64, 1, 7, 128, 256, 64, 64, 3, 64, 200, 64, 300, 1100, 2048, 257, 64]):
         g = torch.Generator().manual_seed(100 + it)
         h_all = [torch.randn(T, H, generator=g).half().cuda() for _ in range(world)]
         res = torch.randn(T, H, generator=g).half().cuda() if it != 1 else None

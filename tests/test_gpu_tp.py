@@ -52,8 +52,10 @@ def _worker(rank, world, port, path, quantize, prompts, n_new, q):
     os._exit(0)
 
 
-@pytest.mark.parametrize("quantize", [None, "gptq"])
-def test_tp2_generate_matches_oracle(tmp_path, quantize):
+@pytest.mark.parametrize("quantize,lens", [(None, [9, 20, 3]), ("gptq", [9, 20, 3]), ("gptq", [200, 150, 90])],
+                         ids=["fp16", "gptq", "gptq-prefill-440-rows"])
+def test_tp2_generate_matches_oracle(tmp_path, quantize, lens):
+    """the 440-row prefill goes through the multi-row blocks of the fused NVLink boundary (more than 256 rows in one step)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from safetensors.torch import save_file
@@ -67,7 +69,7 @@ def test_tp2_generate_matches_oracle(tmp_path, quantize):
         import json
         json.dump({"bits": 4, "group_size": 128}, open(os.path.join(str(tmp_path), "quantize_config.json"), "w"))
     oracle = oll.LlamaOracle(oll.build_shards(ocfg, sd, 2))  # the oracle's own tp = 2 restatement (fp16 partial sums)
-    prompts = _prompts(5, [9, 20, 3], 512)
+    prompts = _prompts(5, lens, 512)
     n_new = 8
     ref, n_exact = _oracle_tokens(oracle, prompts, n_new)
     ctx = mp.get_context("spawn")

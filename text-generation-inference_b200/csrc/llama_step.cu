@@ -44,8 +44,9 @@ static int linear_deferred(const B200Linear* L, const B200LlamaStep* s, const vo
 }
 
 static bool deferring(const B200LlamaStep* s) { return s->defer_splitk && s->gemm_ws && s->T <= 128 && !s->is_prefill; }
-// the fused NVLink boundary takes decode-sized steps; anything larger is all-reduced by the caller between the block calls
-static bool fused_boundary(const B200LlamaWeights* w, const B200LlamaStep* s) { return w->tp_size > 1 && s->p2p_norm && s->T <= 256; }
+// the fused NVLink boundary takes steps of up to 2048 token rows (decode, and prefill chunks of continuous batching); anything
+// larger is all-reduced by the caller between the block calls
+static bool fused_boundary(const B200LlamaWeights* w, const B200LlamaStep* s) { return w->tp_size > 1 && s->p2p_norm && s->T <= 2048; }
 
 #define RUN(expr)            \
   do {                       \
@@ -216,7 +217,7 @@ extern "C" int b200_llama_head(const B200LlamaWeights* w, const B200LlamaStep* s
 // whole step in one call: single rank, or tensor parallel with the fused NVLink boundary (no host-side collective)
 extern "C" int b200_llama_step(const B200LlamaWeights* w, const B200LlamaStep* s, void* stream) {
   if (w->tp_size != 1 && !fused_boundary(w, s)) {
-    b200_set_last_error("llama_step: tensor-parallel ranks without a p2p_norm window (or with T > 256) drive attn/mlp blocks separately "
+    b200_set_last_error("llama_step: tensor-parallel ranks without a p2p_norm window (or with T > 2048) drive attn/mlp blocks separately "
                         "(all-reduce in between)");
     return B200_ERR_UNSUPPORTED;
   }

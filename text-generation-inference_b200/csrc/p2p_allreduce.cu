@@ -141,7 +141,7 @@ p2p_allreduce_f16_kernel(unsigned char* const* __restrict__ peers, __half* __res
 // Nothing downstream ever reads the all-reduced hidden state itself, only norm(hidden + residual) and the new residual, and
 // the residual stream is only ever read by the next boundary.  So the exchange is a reduce-scatter by TOKEN ROW followed by a
 // broadcast of the NORMED row: row t belongs to rank t % world, which alone keeps the residual stream of that row.
-// One block per row t, on every rank:
+// Per row t, on every rank:
 //   1. this rank's partial row (fp16 input, or sum of split-K partials rounded to fp16) -> stored straight into the OWNER's
 //      window (inbox 1: [slot][t / world][source rank][H]), 16-byte stores over NVLink, no flag and no fence
 //   2. owner block: poll inbox 1 until the row of every source rank has landed, add in rank order with fp32 accumulation, ONE
@@ -155,6 +155,10 @@ p2p_allreduce_f16_kernel(unsigned char* const* __restrict__ peers, __half* __res
 // (read only by itself, in an earlier kernel of the stream) for the call after the next; a peer can only write that slot again
 // after it completed the next call, which needs this rank's push of the next call, which is stream-ordered after this
 // kernel.  The per-row call counter lives in the window header and is advanced by the kernel: CUDA-graph replayable.
+// Up to 256 rows every row has its own block; longer steps (prefill chunks up to 2048 rows) give each of <= 256 blocks a run of
+// R = k * world consecutive rows, so every block owns R / world of its rows and the owner work is spread over all blocks.  A
+// block pushes all its partial rows first, then does its owner work, then waits for the rows it does not own: owner work only
+// ever waits for pushes, and all blocks of a launch are resident at once, so the wait graph has no cycle.
 // Every rank computes nothing twice and every rank ends with bit-identical normed rows (they are copies).
 // residual / residual_out are only read / written for the rows this rank owns.
 // ------------------------------------------------------------------------------------------------------------------
@@ -183,138 +187,163 @@ __device__ __forceinline__ uint4 poll_v4(const void* p, unsigned long long t0) {
   return v;
 }
 
-// inbox 1 holds ceil(256 / world) owned rows x world sources <= 256 + 7 rows; both inboxes are laid out for h_cap elements per row
-__host__ __device__ inline int64_t p2p_inbox1_rows(int world) { return (int64_t)((kP2PMaxRows + world - 1) / world) * world; }
+// The fused boundary's own header layout: [kP2PBoundaryRows] u32 per-row call counters.  Inbox 1 holds ceil(rows / world) owned
+// rows x world sources; both inboxes are laid out for h_cap elements per row.
+constexpr int kP2PBoundaryRows = 2048;
+constexpr int kP2PBoundaryGrid = 256;   // blocks of one launch: all resident at once (2 per SM), so no block waits for an unscheduled one
+constexpr int kP2PBoundaryMaxR = 16;    // rows per block
+static_assert(kP2PBoundaryRows * 4 <= kP2PHeaderBytes, "p2p header");
+__host__ __device__ inline int64_t p2p_inbox1_rows(int world) { return (int64_t)((kP2PBoundaryRows + world - 1) / world) * world; }
+// rows per block: one while every row can have its own block, else a multiple of world (every block then owns R / world rows
+// and all blocks share the owner work)
+__host__ __device__ inline int p2p_rows_per_block(int64_t T, int world) {
+  if (T <= kP2PBoundaryGrid) return 1;
+  return world * (int)((T + (int64_t)kP2PBoundaryGrid * world - 1) / ((int64_t)kP2PBoundaryGrid * world));
+}
 
 template <bool kSplitK>
 __global__ void __launch_bounds__(kP2PThreads, 2)
 p2p_allreduce_rmsnorm_kernel(unsigned char* const* __restrict__ peers, const __half* __restrict__ h, const B200SplitK parts,
                              const __half* __restrict__ residual, const __half* __restrict__ gamma, __half* __restrict__ normed,
-                             __half* __restrict__ res_out, int H, int h_cap, float eps, int world, int rank) {
+                             __half* __restrict__ res_out, int T, int R, int H, int h_cap, float eps, int world, int rank) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of the row after the residual add (owner blocks)
+  float* xs = reinterpret_cast<float*>(smem_raw);  // [H] fp32 copy of a row after the residual add (owner work)
   __shared__ float red[32];
-  __shared__ uint32_t s_calls;
+  __shared__ uint32_t s_calls[kP2PBoundaryMaxR];
   pdl_launch_dependents();
-  const int row = blockIdx.x;
-  const int owner = row % world, own_idx = row / world;
+  const int row0 = blockIdx.x * R;
+  const int n_rows = min(R, T - row0);
   unsigned char* mine = peers[rank];
-  uint32_t* my_calls = reinterpret_cast<uint32_t*>(mine) + kP2PMaxRows * kP2PMaxWorld + row;
-  pdl_wait();  // the input is the previous kernel's output; the counter was written by the previous fused launch of the stream
-  if (threadIdx.x == 0) s_calls = *my_calls;
+  uint32_t* my_calls = reinterpret_cast<uint32_t*>(mine);
+  pdl_wait();  // the input is the previous kernel's output; the counters were written by the previous fused launch of the stream
+  if (threadIdx.x < n_rows) s_calls[threadIdx.x] = my_calls[row0 + threadIdx.x];
   __syncthreads();
-  const uint32_t calls = s_calls;
-  const int slot = (int)(calls % 3u), prev = (int)((calls + 2u) % 3u);
   const int64_t row_bytes = (int64_t)h_cap * 2;
   const int64_t in1_rows = p2p_inbox1_rows(world);
   const int64_t in2_base = kP2PHeaderBytes + 3 * in1_rows * row_bytes;
-  auto inbox1 = [&](int sl, int src) { return kP2PHeaderBytes + ((int64_t)sl * in1_rows + (int64_t)own_idx * world + src) * row_bytes; };
-  auto inbox2 = [&](int sl) { return in2_base + ((int64_t)sl * kP2PMaxRows + row) * row_bytes; };
+  auto inbox1 = [&](int sl, int row, int src) {
+    return kP2PHeaderBytes + ((int64_t)sl * in1_rows + (int64_t)(row / world) * world + src) * row_bytes;
+  };
+  auto inbox2 = [&](int sl, int row) { return in2_base + ((int64_t)sl * kP2PBoundaryRows + row) * row_bytes; };
   const uint4 blank = make_uint4(kP2PUnwritten, kP2PUnwritten, kP2PUnwritten, kP2PUnwritten);
 
-  // 1. this rank's partial row -> the owner's inbox 1
-  unsigned char* to_owner = peers[owner] + inbox1(slot, rank);
-  for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
-    uint4 v;
-    if constexpr (kSplitK) {
-      const float4 a = splitk_sum4(parts, row, i), b = splitk_sum4(parts, row, i + 4);
-      v.x = pack_half2(a.x, a.y);
-      v.y = pack_half2(a.z, a.w);
-      v.z = pack_half2(b.x, b.y);
-      v.w = pack_half2(b.z, b.w);
-    } else {
-      v = *reinterpret_cast<const uint4*>(h + (size_t)row * H + i);
+  // 1. this rank's partial rows -> their owners' inbox 1 (nothing here waits)
+  for (int j = 0; j < n_rows; ++j) {
+    const int row = row0 + j;
+    unsigned char* to_owner = peers[row % world] + inbox1((int)(s_calls[j] % 3u), row, rank);
+    for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
+      uint4 v;
+      if constexpr (kSplitK) {
+        const float4 a = splitk_sum4(parts, row, i), b = splitk_sum4(parts, row, i + 4);
+        v.x = pack_half2(a.x, a.y);
+        v.y = pack_half2(a.z, a.w);
+        v.z = pack_half2(b.x, b.y);
+        v.w = pack_half2(b.z, b.w);
+      } else {
+        v = *reinterpret_cast<const uint4*>(h + (size_t)row * H + i);
+      }
+      st_peer_v4(to_owner + (int64_t)i * 2, no_neg_zero(v));
     }
-    st_peer_v4(to_owner + (int64_t)i * 2, no_neg_zero(v));
   }
   const unsigned long long t0 = global_timer_ns();
 
-  if (rank != owner) {
-    // clear the slot of this row's previous call while the owner works, then wait for the normed row
-    unsigned char* old = mine + inbox2(prev);
-    for (int i = threadIdx.x * 8; i < h_cap; i += kP2PThreads * 8) *reinterpret_cast<uint4*>(old + (int64_t)i * 2) = blank;
-    const unsigned char* in = mine + inbox2(slot);
-    for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8)
-      *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = poll_v4(in + (int64_t)i * 2, t0);
-    if (threadIdx.x == 0) *my_calls = calls + 1;
-    return;
+  // 2. the rows this rank owns: sum in rank order, residual add, RMSNorm, normed row to everyone (waits for step 1 of the
+  //    same block index on the other ranks only)
+  for (int j = 0; j < n_rows; ++j) {
+    const int row = row0 + j;
+    if (row % world != rank) continue;
+    const int slot = (int)(s_calls[j] % 3u), prev = (int)((s_calls[j] + 2u) % 3u);
+    float ss = 0.f;
+    for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      uint4 ld[kP2PMaxWorld];
+#pragma unroll
+      for (int r = 0; r < kP2PMaxWorld; ++r)
+        if (r < world) ld[r] = ld_peer_v4(mine + inbox1(slot, row, r) + (int64_t)i * 2);  // all sources in flight together
+#pragma unroll
+      for (int r = 0; r < kP2PMaxWorld; ++r)
+        if (r < world) {
+          if (!landed(ld[r])) ld[r] = poll_v4(mine + inbox1(slot, row, r) + (int64_t)i * 2, t0);
+          add_h8(acc, ld[r]);
+        }
+      float x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = __half2float(__float2half_rn(acc[k]));  // the all-reduce result is an fp16 tensor
+      uint4 ov;
+      __half2* o2 = reinterpret_cast<__half2*>(&ov);
+      if (residual) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(residual + (size_t)row * H + i);
+        const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(r2[k]);
+          x[2 * k] += f.x;
+          x[2 * k + 1] += f.y;
+        }
+      }
+      // residual == NULL (first layer, flash_llama_modeling.py:149-150): residual_out = the reduced hidden state itself
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o2[k] = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+      *reinterpret_cast<uint4*>(res_out + (size_t)row * H + i) = ov;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xs[i + k] = x[k];
+        ss += x[k] * x[k];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    __syncthreads();  // red[] of the previous owned row has been read by everyone
+    if (lane_id() == 0) red[warp_id()] = ss;
+    __syncthreads();
+    if (warp_id() == 0) {
+      float v = lane_id() < kP2PThreads / 32 ? red[lane_id()] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane_id() == 0) red[0] = v;
+    }
+    __syncthreads();
+    const float rstd = rsqrtf(red[0] / (float)H + eps);
+    const int64_t out_off = inbox2(slot, row);
+    for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
+      const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
+      const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+      uint4 ov;
+      __half2* o2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 g = __half22float2(g2[k]);
+        o2[k] = __floats2half2_rn(xs[i + 2 * k] * rstd * g.x, xs[i + 2 * k + 1] * rstd * g.y);
+      }
+      ov = no_neg_zero(ov);
+      for (int r = 1; r < world; ++r) {  // peers first, starting with the next rank: the ranks' pushes spread over the links
+        const int dst = rank + r < world ? rank + r : rank + r - world;
+        st_peer_v4(peers[dst] + out_off + (int64_t)i * 2, ov);
+      }
+      *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = ov;
+    }
+    // clear inbox 1 of this row's previous call (all sources); each thread re-reads only its own xs[] entries, no barrier needed
+    for (int r = 0; r < world; ++r) {
+      unsigned char* old = mine + inbox1(prev, row, r);
+      for (int i = threadIdx.x * 8; i < h_cap; i += kP2PThreads * 8) *reinterpret_cast<uint4*>(old + (int64_t)i * 2) = blank;
+    }
   }
 
-  // 2. owner: sum in rank order, residual add, statistics
-  float ss = 0.f;
-  for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    uint4 ld[kP2PMaxWorld];
-#pragma unroll
-    for (int r = 0; r < kP2PMaxWorld; ++r)
-      if (r < world) ld[r] = ld_peer_v4(mine + inbox1(slot, r) + (int64_t)i * 2);  // all sources in flight together
-#pragma unroll
-    for (int r = 0; r < kP2PMaxWorld; ++r)
-      if (r < world) {
-        if (!landed(ld[r])) ld[r] = poll_v4(mine + inbox1(slot, r) + (int64_t)i * 2, t0);
-        add_h8(acc, ld[r]);
-      }
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = __half2float(__float2half_rn(acc[j]));  // the all-reduce result is an fp16 tensor
-    uint4 ov;
-    __half2* o2 = reinterpret_cast<__half2*>(&ov);
-    if (residual) {
-      const uint4 rv = *reinterpret_cast<const uint4*>(residual + (size_t)row * H + i);
-      const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(r2[j]);
-        x[2 * j] += f.x;
-        x[2 * j + 1] += f.y;
-      }
-    }
-    // residual == NULL (first layer, flash_llama_modeling.py:149-150): residual_out = the reduced hidden state itself
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-    *reinterpret_cast<uint4*>(res_out + (size_t)row * H + i) = ov;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      xs[i + j] = x[j];
-      ss += x[j] * x[j];
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane_id() == 0) red[warp_id()] = ss;
-  __syncthreads();
-  if (warp_id() == 0) {
-    float v = lane_id() < kP2PThreads / 32 ? red[lane_id()] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane_id() == 0) red[0] = v;
-  }
-  __syncthreads();
-  const float rstd = rsqrtf(red[0] / (float)H + eps);
-  const int64_t out_off = inbox2(slot);
-  for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8) {
-    const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
-    const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
-    uint4 ov;
-    __half2* o2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 g = __half22float2(g2[j]);
-      o2[j] = __floats2half2_rn(xs[i + 2 * j] * rstd * g.x, xs[i + 2 * j + 1] * rstd * g.y);
-    }
-    ov = no_neg_zero(ov);
-    for (int r = 1; r < world; ++r) {  // peers first, starting with the next rank: the ranks' pushes spread over the links
-      const int dst = rank + r < world ? rank + r : rank + r - world;
-      st_peer_v4(peers[dst] + out_off + (int64_t)i * 2, ov);
-    }
-    *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = ov;
-  }
-  // clear inbox 1 of this row's previous call (all sources)
-  for (int r = 0; r < world; ++r) {
-    unsigned char* old = mine + inbox1(prev, r);
+  // 3. the other rows: clear the cell of the row's previous call, then wait for the owner's normed row
+  for (int j = 0; j < n_rows; ++j) {
+    const int row = row0 + j;
+    if (row % world == rank) continue;
+    unsigned char* old = mine + inbox2((int)((s_calls[j] + 2u) % 3u), row);
     for (int i = threadIdx.x * 8; i < h_cap; i += kP2PThreads * 8) *reinterpret_cast<uint4*>(old + (int64_t)i * 2) = blank;
   }
-  if (threadIdx.x == 0) *my_calls = calls + 1;
+  for (int j = 0; j < n_rows; ++j) {
+    const int row = row0 + j;
+    if (row % world == rank) continue;
+    const unsigned char* in = mine + inbox2((int)(s_calls[j] % 3u), row);
+    for (int i = threadIdx.x * 8; i < H; i += kP2PThreads * 8)
+      *reinterpret_cast<uint4*>(normed + (size_t)row * H + i) = poll_v4(in + (int64_t)i * 2, t0);
+  }
+  if (threadIdx.x < n_rows) my_calls[row0 + threadIdx.x] = s_calls[threadIdx.x] + 1;
 }
 
 __global__ void p2p_fill_kernel(uint4* p, int64_t n, uint32_t word) {
@@ -438,7 +467,7 @@ extern "C" int b200_p2p_create(int64_t max_bytes, int world, int rank, void** ct
   ctx->rank = rank;
   ctx->max_bytes = (max_bytes + kP2PChunkBytes - 1) / kP2PChunkBytes * kP2PChunkBytes;
   // the chunked all-reduce and the arg-max use two slots of max_bytes; the fused boundary uses 3 slots x (inbox 1 + inbox 2),
-  // each 256 (+ up to 7) rows of max_bytes / 256, and wants every data cell to read "unwritten" (fp16 -0.0) before its first call
+  // each 2048 (+ up to 7) rows of max_bytes / 2048, and wants every data cell to read "unwritten" (fp16 -0.0) before its first call
   const size_t bytes = kP2PHeaderBytes + 7 * (size_t)ctx->max_bytes;
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaMalloc(&ctx->window, bytes);
@@ -510,7 +539,7 @@ extern "C" int b200_p2p_allreduce_f16(void* ctx_, void* data, int64_t n, void* s
 // row-parallel GEMM, H = h_parts->N, T = h_parts->T) is given.  residual may be NULL (first layer): residual_out then receives
 // the reduced hidden state.  residual / residual_out are read / written ONLY for the rows this rank owns (t % world == rank):
 // the residual stream of a row lives on its owner, every rank gets every normed row.  All boundaries of a step must go through
-// this call for that to hold.  T <= 256, 256 * H * 2 <= max_bytes, H % 8 == 0, H <= 16384.
+// this call for that to hold.  T <= 2048, 2048 * H * 2 <= max_bytes, H % 8 == 0, H <= 16384.
 extern "C" int b200_p2p_allreduce_rmsnorm(void* ctx_, const void* h, const B200SplitK* h_parts, const void* residual, const void* gamma,
                                           void* normed_out, void* residual_out, int64_t T, int64_t H, float eps, void* stream) {
   P2PContext* ctx = (P2PContext*)ctx_;
@@ -527,12 +556,14 @@ extern "C" int b200_p2p_allreduce_rmsnorm(void* ctx_, const void* h, const B200S
     H = h_parts->N;
   }
   if (T == 0) return B200_OK;
-  // the window is laid out for rows of h_cap elements: 3 x (256 + 7) + 3 x 256 rows fit in the 7 * max_bytes behind the header
-  const int64_t h_cap = ctx->max_bytes / (2 * kP2PMaxRows) / 8 * 8;
-  if (T > kP2PMaxRows || H % 8 != 0 || H > 16384 || H > h_cap || (h && ((uintptr_t)h & 15) != 0)) {
-    b200_set_last_error("p2p_allreduce_rmsnorm: need T <= 256, H % 8 == 0, H <= 16384, 256 * H * 2 <= max_bytes, 16-byte aligned h");
+  // the window is laid out for 2048 rows of h_cap elements: 3 x (2048 + 7) + 3 x 2048 rows fit in the 7 * max_bytes behind the header
+  const int64_t h_cap = ctx->max_bytes / (2 * kP2PBoundaryRows) / 8 * 8;
+  if (T > kP2PBoundaryRows || H % 8 != 0 || H > 16384 || H > h_cap || (h && ((uintptr_t)h & 15) != 0)) {
+    b200_set_last_error("p2p_allreduce_rmsnorm: need T <= 2048, H % 8 == 0, H <= 16384, 2048 * H * 2 <= max_bytes, 16-byte aligned h");
     return B200_ERR_ARG;
   }
+  const int R = p2p_rows_per_block(T, ctx->world);
+  const unsigned grid = (unsigned)((T + R - 1) / R);
   for (int r = 0; r < ctx->world; ++r)
     if (!ctx->peer[r]) { b200_set_last_error("p2p_allreduce_rmsnorm: b200_p2p_connect has not run"); return B200_ERR_ARG; }
   if (ctx->family == 1) { b200_set_last_error("p2p_allreduce_rmsnorm: this window already serves b200_p2p_allreduce_f16"); return B200_ERR_ARG; }
@@ -542,15 +573,15 @@ extern "C" int b200_p2p_allreduce_rmsnorm(void* ctx_, const void* h, const B200S
   if (h_parts) {
     constexpr auto kernel = p2p_allreduce_rmsnorm_kernel<true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel<splitk>", kernel, dim3((unsigned)T), dim3(kP2PThreads), smem, st,
+    B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel<splitk>", kernel, dim3(grid), dim3(kP2PThreads), smem, st,
                    (unsigned char* const*)ctx->peer_table, (const __half*)nullptr, *h_parts, (const __half*)residual, (const __half*)gamma,
-                   (__half*)normed_out, (__half*)residual_out, (int)H, (int)h_cap, eps, ctx->world, ctx->rank);
+                   (__half*)normed_out, (__half*)residual_out, (int)T, R, (int)H, (int)h_cap, eps, ctx->world, ctx->rank);
   } else {
     constexpr auto kernel = p2p_allreduce_rmsnorm_kernel<false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel", kernel, dim3((unsigned)T), dim3(kP2PThreads), smem, st,
+    B200_LAUNCH_AS("p2p_allreduce_rmsnorm_kernel", kernel, dim3(grid), dim3(kP2PThreads), smem, st,
                    (unsigned char* const*)ctx->peer_table, (const __half*)h, B200SplitK{}, (const __half*)residual, (const __half*)gamma,
-                   (__half*)normed_out, (__half*)residual_out, (int)H, (int)h_cap, eps, ctx->world, ctx->rank);
+                   (__half*)normed_out, (__half*)residual_out, (int)T, R, (int)H, (int)h_cap, eps, ctx->world, ctx->rank);
   }
   b200_count_launches(1);
   return B200_OK;

@@ -44,10 +44,11 @@ def _open_window(process_group, max_bytes: int):
 
 
 class FusedBoundary:
-    """Windows for the in-step layer boundary.  `norm` serves b200_p2p_allreduce_rmsnorm for up to `max_rows` token rows of
-    `hidden_size`; `argmax` serves b200_p2p_argmax.  Both are None when the group has one rank or p2p is switched off."""
+    """Windows for the in-step layer boundary.  `norm` serves b200_p2p_allreduce_rmsnorm for up to MAX_ROWS token rows of
+    `hidden_size` (decode steps and the prefill chunks of continuous batching; 7 x MAX_ROWS x hidden x 2 bytes per rank);
+    `argmax` serves b200_p2p_argmax.  Both are None when the group has one rank or p2p is switched off."""
 
-    MAX_ROWS = 256
+    MAX_ROWS = 2048
 
     def __init__(self, process_group, hidden_size: int):
         self.norm = self.argmax = None

@@ -23,9 +23,9 @@ def main():
     group = initialize_torch_distributed(world, rank)
     lib = _lib.load()
     reps = 40
-    for T, H in [(64, 4096), (128, 8192), (1, 4096), (16, 4096), (256, 4096), (256, 8192)]:
+    for T, H in [(64, 4096), (128, 8192), (1, 4096), (256, 8192), (512, 8192), (1100, 8192), (2048, 8192), (2048, 4096)]:
         fb = FusedBoundary(group, H)
-        one = LayerBoundaryAllReduce(group, max_bytes=256 * H * 2)
+        one = LayerBoundaryAllReduce(group, max_bytes=2048 * H * 2)
         g = torch.Generator().manual_seed(rank)
         h = torch.randn(T, H, generator=g).half().cuda()
         res = torch.randn(T, H, generator=g).half().cuda()
