@@ -29,12 +29,6 @@ from .types import Batch, GenerateError
 
 USE_CUDA_GRAPHS = __import__("os").getenv("B200_CUDA_GRAPHS", "true").lower() != "false"
 FUSED_CHOOSER = __import__("os").getenv("B200_FUSED_CHOOSER", "1") != "0"
-# When to capture the step of a batch into a CUDA graph.  Capture + instantiation costs about six replays' worth of saved launch
-# overhead: a batch is captured after 2 steps when it is new or its predecessor (the batch it was pruned / concatenated from)
-# lived long, and only after GRAPH_AFTER_STEPS_CHURN steps when the predecessor was pruned / concatenated away within
-# GRAPH_STABLE_LIFE steps (continuous batching with requests arriving and completing every few steps: most batch states die
-# before a graph would have paid for itself).
-GRAPH_AFTER_STEPS, GRAPH_AFTER_STEPS_CHURN, GRAPH_STABLE_LIFE = 2, 8, 12
 
 
 @dataclass
@@ -175,16 +169,12 @@ class FlashCausalLMBatch(Batch):
         lens_t = torch.tensor([0] + input_lengths, dtype=torch.int32, device=device)
         kv = PagedKVState(sequence_ids=seq_ids, block_table=torch.cat(tables).contiguous(), context_lens=torch.cat(ctx),
                           slot_mapping=torch.empty(new_bs, dtype=torch.int64, device=device), max_blocks=max_cols)
-        merged = FlashCausalLMBatch(
+        return FlashCausalLMBatch(
             batch_id=first.batch_id, requests=requests, input_ids=torch.cat(input_ids), inputs_embeds=None,
             position_ids=torch.cat(position_ids), cu_seqlens=torch.cumsum(lens_t, 0, dtype=torch.int32),
             cu_seqlens_q=torch.arange(new_bs + 1, device=device, dtype=torch.int32), max_seqlen=max_seqlen, past_key_values=kv,
             input_lengths=input_lengths, total_lengths=total_lengths, all_input_ids_tensor=all_ids, next_token_chooser=chooser,
             pad_token_id=first.pad_token_id, kv_cache_manager=first.kv_cache_manager)
-        lives = [b._fused["steps"] for b in batches if getattr(b, "_fused", None)]
-        if lives:
-            merged._fused_life_hint = min(lives)  # how long the running batch lasted: the CUDA-graph capture policy reads it
-        return merged
 
     @classmethod
     def prune(cls, batch: "FlashCausalLMBatch", completed_ids: List[int]) -> Optional["FlashCausalLMBatch"]:
@@ -337,8 +327,6 @@ class FlashCausalLM(Model):
                       logits=torch.empty(B, V, dtype=torch.float16, device=self.device),
                       banned=torch.full((B,), -1, dtype=torch.int64, device=self.device), banned_host=[-1] * B,
                       steps=0, graph=None, max_s_cap=0)
-            last_life = st_old["steps"] if (st_old := getattr(batch, "_fused", None)) else getattr(batch, "_fused_life_hint", None)
-            st["graph_after"] = GRAPH_AFTER_STEPS if last_life is None or last_life >= GRAPH_STABLE_LIFE else GRAPH_AFTER_STEPS_CHURN
             tp = getattr(self.engine, "world_size", 1)
             plain = chooser.is_plain_greedy and not any(r.details.logprobs or r.details.ranks for r in batch.requests)
             st["device_chooser"] = None if plain else chooser.device_chooser()
@@ -424,7 +412,10 @@ class FlashCausalLM(Model):
             batch.all_input_ids_tensor.scatter_(dim=1, index=batch.position_ids[:, None], src=st["next_ids"][:, None])
             batch.cu_seqlens.add_(batch.cu_seqlens_q)
 
-        if use_graph and st["steps"] >= st.get("graph_after", GRAPH_AFTER_STEPS) and USE_CUDA_GRAPHS:
+        # Captured from the third step of a batch state on.  Measured on the 8B continuous-batching session (a state lives 2-3
+        # steps on average there): capturing after 2 steps 11.2 k tokens/s, only after 8 stable steps 9.6 k, after 1 step 9.3 k
+        # (same box, profiles/r2_graph_capture_policy.txt) - the eager step is host-bound enough that even short-lived graphs pay.
+        if use_graph and st["steps"] >= 2 and USE_CUDA_GRAPHS:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 enqueue()
