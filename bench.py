@@ -52,6 +52,8 @@ WORKLOADS = {
     "llama2-7b-gptq": ("llama-2-7b", "gptq", 64, 1024, 2048),
     "llama2-7b-fp16": ("llama-2-7b", None, 64, 1024, 2048),
     "llama3-70b-gptq": ("llama-3-70b", "gptq", 128, 512, 1024),  # steady-state sibling of config[4]; needs --gpus 2 or more
+    "pythia-12b-fp16": ("pythia-12b", None, 64, 1024, 2048),  # GPT-NeoX, the second flash family (parallel residual, partial rotary)
+    "tiny-neox": ("tiny-neox", None, 4, 32, 256),
     "tinyllama-fp16": ("tinyllama-1.1b", None, 32, 512, 1024),
     "tiny-test": ("tiny-test", None, 4, 32, 256),
 }
@@ -178,10 +180,10 @@ def build_model(workload, world, rank, num_layers=None, cfg_override=None, weigh
     from tgis_b200.inference_engine import InferenceEngine
     from tgis_b200.models.flash_causal_lm import FlashCausalLM
     from tgis_b200.utils.dist import initialize_torch_distributed
-    from tgis_b200.utils.synthetic import SyntheticWeights, llama_config, make_tokenizer
+    from tgis_b200.utils.synthetic import SyntheticWeights, make_tokenizer, model_config
 
     arch, quantize, B, L0, L1 = WORKLOADS[workload]
-    cfg = cfg_override or llama_config(arch, quantize=quantize, max_position_embeddings=max(4096, L1 + 64), num_layers=num_layers)
+    cfg = cfg_override or model_config(arch, quantize=quantize, max_position_embeddings=max(4096, L1 + 64), num_layers=num_layers)
     local = int(os.getenv("LOCAL_RANK", rank))
     torch.cuda.set_device(local % torch.cuda.device_count())
     device = torch.device("cuda", torch.cuda.current_device())
@@ -211,7 +213,8 @@ def algorithmic_bytes_per_step(cfg, quantize, B, ctx, tp):
     H, I, V, nl = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers
     d = H // cfg.num_attention_heads
     h, kv = cfg.num_attention_heads, cfg.num_key_value_heads
-    lin_params = nl * ((h + 2 * kv) * d * H + h * d * H + 2 * I * H + I * H)
+    mlp_mats = 2 if getattr(cfg, "model_type", "llama") == "gpt_neox" else 3  # h_to_4h, 4h_to_h | gate, up, down
+    lin_params = nl * ((h + 2 * kv) * d * H + h * d * H + mlp_mats * I * H)
     if quantize == "gptq":
         w_lin = lin_params * (0.5 + (2 + 0.5) / 128)
     else:
@@ -625,12 +628,14 @@ def run_gpu(args, workload):
         except Exception as e:  # noqa: BLE001
             extra[other] = {"failed": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        if world == 1 and not args.no_extra:
+        from tgis_b200.utils.synthetic import ARCHS as LLAMA_ARCHS
+        llama_family = arch in LLAMA_ARCHS  # the self-check and the CPU arm restate the Llama graph
+        if world == 1 and not args.no_extra and llama_family:
             try:
                 line["self_check"] = self_check(arch, quantize)
             except Exception as e:  # noqa: BLE001
                 line["self_check"] = {"failed": f"{type(e).__name__}: {e}"}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and llama_family:
             try:
                 r = cpu_reference_decode(arch, B, (L0 + L1) // 2, max(2, min(4, args.steps)), 1, args.cpu_layers)
                 line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}

@@ -54,3 +54,21 @@ def test_neox_engine_registers_the_family():
     import tgis_b200  # noqa: F401
     from tgis_b200 import inference_engine
     assert "gpt_neox" in inference_engine.FLASH_TYPES and "llama" in inference_engine.FLASH_TYPES
+
+
+def test_synthetic_neox_checkpoint_serves_every_tensor_the_model_loads():
+    """bench.py's GPT-NeoX workload builds the model from utils/synthetic.py: every name the loader asks for exists, at tp 1 and 2"""
+    import torch
+    import tgis_b200  # noqa: F401
+    from tgis_b200.models.custom_modeling.flash_neox_modeling import FlashGPTNeoXForCausalLM
+    from tgis_b200.utils.dist import FakeGroup
+    from tgis_b200.utils.synthetic import SyntheticWeights, model_config
+    cfg = model_config("tiny-neox", quantize=None, max_position_embeddings=512)
+    sizes = []
+    for world in (1, 2):
+        model = FlashGPTNeoXForCausalLM(cfg, SyntheticWeights(cfg, "cpu", torch.float16, FakeGroup(0, world)))
+        qkv = model.model.layers[0].attention.query_key_value
+        sizes.append(tuple(qkv.weight.shape))
+        inv = model.model.layers[0].attention.rotary_emb.inv_freq
+        assert inv.dtype == torch.float32 and inv.shape[0] == int(64 * 0.25) // 2
+    assert sizes == [(768, 256), (384, 256)]

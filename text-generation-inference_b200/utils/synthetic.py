@@ -21,6 +21,11 @@ ARCHS = {
     "llama-3-70b": (8192, 28672, 80, 64, 8, 128256),
     "tiny-test": (256, 512, 2, 4, 2, 512),
 }
+NEOX_ARCHS = {
+    # name: (hidden, intermediate, layers, heads, vocab, rotary_pct)
+    "pythia-12b": (5120, 20480, 36, 40, 50688, 0.25),  # head size 128 (gpt-neox-20b's 96 is not a kernel instantiation)
+    "tiny-neox": (256, 1024, 2, 4, 512, 0.25),
+}
 
 
 def llama_config(name: str, quantize: Optional[str] = None, max_position_embeddings: int = 4096, num_layers: Optional[int] = None):
@@ -32,6 +37,26 @@ def llama_config(name: str, quantize: Optional[str] = None, max_position_embeddi
         eos_token_id=2, pad_token_id=0, bos_token_id=1, quantize=quantize, name=name)
     cfg.to_dict = lambda: {k: v for k, v in vars(cfg).items() if not callable(v)}
     return cfg
+
+
+def neox_config(name: str, max_position_embeddings: int = 2048, num_layers: Optional[int] = None):
+    """GPT-NeoX (the second tensor-parallel flash family, flash_neox_modeling.py): parallel residual, partial rotary, biases."""
+    H, I, L, h, V, pct = NEOX_ARCHS[name]
+    cfg = types.SimpleNamespace(
+        model_type="gpt_neox", hidden_size=H, intermediate_size=I, num_hidden_layers=num_layers or L, num_attention_heads=h,
+        num_key_value_heads=h, vocab_size=V, rotary_pct=pct, rotary_emb_base=10000.0, layer_norm_eps=1e-5,
+        use_parallel_residual=True, hidden_act="gelu_fast", max_position_embeddings=max_position_embeddings,
+        tie_word_embeddings=False, eos_token_id=2, pad_token_id=0, bos_token_id=1, quantize=None, name=name)
+    cfg.to_dict = lambda: {k: v for k, v in vars(cfg).items() if not callable(v)}
+    return cfg
+
+
+def model_config(name: str, **kw):
+    """config of a named synthetic architecture of either family"""
+    if name in NEOX_ARCHS:
+        kw.pop("quantize", None)
+        return neox_config(name, **kw)
+    return llama_config(name, **kw)
 
 
 class SyntheticWeights(Weights):
@@ -51,6 +76,13 @@ class SyntheticWeights(Weights):
     def _linear_shape(self, name: str) -> Tuple[int, int]:
         c = self.cfg
         d = c.hidden_size // c.num_attention_heads
+        if getattr(c, "model_type", "llama") == "gpt_neox":
+            table = {"query_key_value": (3 * c.hidden_size, c.hidden_size), "attention.dense": (c.hidden_size, c.hidden_size),
+                     "dense_h_to_4h": (c.intermediate_size, c.hidden_size), "dense_4h_to_h": (c.hidden_size, c.intermediate_size)}
+            for k, v in table.items():
+                if f".{k}." in name:
+                    return v
+            raise RuntimeError(f"weight {name} does not exist")
         table = {"q_proj": (c.num_attention_heads * d, c.hidden_size), "k_proj": (c.num_key_value_heads * d, c.hidden_size),
                  "v_proj": (c.num_key_value_heads * d, c.hidden_size), "o_proj": (c.hidden_size, c.num_attention_heads * d),
                  "gate_proj": (c.intermediate_size, c.hidden_size), "up_proj": (c.intermediate_size, c.hidden_size),
@@ -62,10 +94,14 @@ class SyntheticWeights(Weights):
 
     def get_shape(self, tensor_name: str):
         c = self.cfg
-        if tensor_name in ("model.embed_tokens.weight", "lm_head.weight"):
+        if tensor_name in ("model.embed_tokens.weight", "lm_head.weight", "gpt_neox.embed_in.weight", "embed_out.weight"):
             return [c.vocab_size, c.hidden_size]
-        if tensor_name.endswith("layernorm.weight") or tensor_name == "model.norm.weight":
+        if self._is_norm(tensor_name):
             return [c.hidden_size]
+        if tensor_name.endswith("rotary_emb.inv_freq"):
+            return [int(c.hidden_size // c.num_attention_heads * c.rotary_pct) // 2]
+        if tensor_name.endswith(".bias"):
+            return [self._linear_shape(tensor_name)[0]]
         n, k = self._linear_shape(tensor_name)
         g = self.gptq_groupsize if self.gptq_groupsize > 0 else k
         if tensor_name.endswith(".weight"):
@@ -80,6 +116,11 @@ class SyntheticWeights(Weights):
             return [k]
         raise RuntimeError(f"weight {tensor_name} does not exist")
 
+    @staticmethod
+    def _is_norm(tensor_name: str) -> bool:
+        stem = tensor_name.rsplit(".", 1)[0]
+        return stem.endswith(("layernorm", "layer_norm")) or tensor_name == "model.norm.weight"
+
     # -- generation ------------------------------------------------------------------------------
     def _full(self, tensor_name: str) -> torch.Tensor:
         if tensor_name == "gptq_bits":
@@ -88,8 +129,12 @@ class SyntheticWeights(Weights):
             return torch.tensor(self.gptq_groupsize)
         shape = self.get_shape(tensor_name)
         gen = torch.Generator(device=self.device).manual_seed(self.seed * 1000003 + zlib.crc32(tensor_name.encode()))
-        if tensor_name.endswith("layernorm.weight") or tensor_name == "model.norm.weight":
-            return torch.ones(shape, dtype=self.dtype, device=self.device)
+        if self._is_norm(tensor_name):
+            fill = torch.zeros if tensor_name.endswith(".bias") else torch.ones
+            return fill(shape, dtype=self.dtype, device=self.device)
+        if tensor_name.endswith("rotary_emb.inv_freq"):
+            rot = 2 * shape[0]
+            return 1.0 / (self.cfg.rotary_emb_base ** (torch.arange(0, rot, 2, device=self.device, dtype=torch.float32) / rot))
         if tensor_name.endswith((".qweight", ".qzeros")):
             return torch.randint(-2 ** 31, 2 ** 31 - 1, shape, generator=gen, device=self.device, dtype=torch.int32)
         if tensor_name.endswith(".scales"):
