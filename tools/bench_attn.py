@@ -38,11 +38,14 @@ def timeit(fn, n=4, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
+    ap.add_argument("--decode-only", action="store_true")
     a = ap.parse_args()
     lines = []
     g = torch.Generator(device=dev).manual_seed(0)
     for name, B, L, h, kv, d in [("llama3-8b prefill", 64, 1024, 32, 8, 128), ("llama2-7b prefill", 64, 1024, 32, 32, 128),
                                  ("tinyllama prefill", 32, 512, 32, 4, 64), ("8b add-on prefill 16 x 640", 16, 640, 32, 8, 128)]:
+        if a.decode_only:
+            break
         T = B * L
         qkv = torch.randn(T, (h + 2 * kv) * d, device=dev, generator=g).half()
         q = qkv[:, :h * d].view(T, h, d)
