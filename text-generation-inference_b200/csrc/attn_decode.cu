@@ -309,7 +309,9 @@ extern "C" int b200_attn_decode_paged(const void* q, int64_t q_token_stride, con
     return B200_ERR_ARG;
   }
   if ((q_token_stride & 1) || ((uintptr_t)q & 3)) { b200_set_last_error("attn_decode_paged: q must be 4-byte aligned"); return B200_ERR_ARG; }
-  // split-KV granularity: the largest chunk size that still gives every SM several CTAs (2 resident CTAs x 148 SMs), then
+  // split-KV granularity: the largest chunk size that still gives every SM a CTA (measured, profiles/r2_attn_chunk_sweep.txt:
+  // asking for more CTAs than that - this used to be 4 x 296 - cuts tensor-parallel shards, whose B * n_kv is small, into
+  // 128-token chunks whose per-CTA set-up dominates: 8B tp4 30.6 -> 23.0 us, 70B tp8 32.9 -> 24.2 us per launch), then
   // EQUAL chunks of that count (page aligned): with a fixed 512 a context of 1563 tokens would be cut 512/512/512/27 and the
   // last quarter of the CTAs would do almost nothing while the others set the kernel's duration
   int target = kMaxChunkTokens;
@@ -321,7 +323,12 @@ extern "C" int b200_attn_decode_paged(const void* q, int64_t q_token_stride, con
     }
     if (env_target >= kMinChunkTokens && env_target <= kMaxChunkTokens) target = env_target;
   }
-  while (target > kMinChunkTokens && (int64_t)B * n_kv_heads * ((max_context_len + target - 1) / target) < 4 * 296) target >>= 1;
+  static int min_ctas = -1;
+  if (min_ctas < 0) {
+    const char* e = getenv("B200_ATTN_MIN_CTAS");
+    min_ctas = e ? atoi(e) : 148;
+  }
+  while (target > kMinChunkTokens && (int64_t)B * n_kv_heads * ((max_context_len + target - 1) / target) < min_ctas) target >>= 1;
   int n_chunks = (max_context_len + target - 1) / target;
   if (n_chunks < 1) n_chunks = 1;
   int chunk_tokens = ((max_context_len + n_chunks - 1) / n_chunks + kPageTokens - 1) / kPageTokens * kPageTokens;

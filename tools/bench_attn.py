@@ -66,8 +66,9 @@ def main():
                      f"paged tcgen05 {t_new:9.1f} us ({flops / t_new / 1e6:7.1f} TFLOP/s)")
         del qkv, k_pool, v_pool
     for name, B, L, h, kv, d in [("llama3-8b decode", 64, 1549, 32, 8, 128), ("llama2-7b decode", 64, 1549, 32, 32, 128),
-                                 ("8b tp2 decode", 64, 1549, 16, 4, 128), ("8b tp8 decode", 64, 1549, 4, 1, 128),
-                                 ("70b tp8 decode bs128", 128, 1536, 8, 1, 128)]:
+                                 ("8b tp2 decode", 64, 1549, 16, 4, 128), ("8b tp4 decode", 64, 1549, 8, 2, 128),
+                                 ("8b tp8 decode", 64, 1549, 4, 1, 128), ("70b tp8 decode bs128", 128, 1536, 8, 1, 128),
+                                 ("70b tp8 decode bs96 ctx768", 96, 768, 8, 1, 128), ("7b fp16 tp8 decode", 64, 1549, 4, 4, 128)]:
         pages = (2048 + 15) // 16
         k_pool, v_pool = ops.kv_pool_alloc(B * pages + 1, kv, d, dev)
         k_pool.normal_(generator=g)
