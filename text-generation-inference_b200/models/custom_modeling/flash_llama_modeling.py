@@ -210,6 +210,8 @@ class FlashLlamaForCausalLM(nn.Module):
         if n > rot._seq_len_cached:
             n = max(n, 2 * rot._seq_len_cached)  # grow geometrically: pointers in the C struct must stay stable
             self._cw = None
+            # cached step structs and captured CUDA graphs hold the old tables' pointers: FlashCausalLM keys them on this version
+            self.scratch.version += 1
         return rot.tables(n, torch.float16, self.device)
 
     def c_weights(self, max_s: int = 0) -> _lib.B200LlamaWeights:
