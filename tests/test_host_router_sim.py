@@ -80,3 +80,28 @@ def test_router_sim_respects_arrival_times():
     # arrivals are ~1 s apart and a fake RPC takes microseconds: no two requests ever run together
     assert out["stats"]["max_batch"] == 1 and out["stats"]["prefill_calls"] == 5
     assert out["stats"]["sim_time_s"] >= reqs[-1].arrival_s
+
+
+def test_router_sim_ranks_agree_on_the_clock():
+    """With several shards every rank runs the loop itself; `agree` replaces each RPC's measured time by one all ranks share, so
+    two ranks whose own clocks differ wildly still admit the same requests at the same steps."""
+    def session(own_speed):
+        shard = FakeShard()
+        reqs = router_sim.make_requests(40, rate_per_s=20.0, prompt_range=(1, 9), new_range=(2, 9), vocab=50, seed=11)
+        calls = []
+        ticks = iter(range(10 ** 6))
+
+        def agree(dt):
+            assert dt >= 0.0
+            calls.append(dt * own_speed)       # what this rank measured does not matter ...
+            return 0.013 + 0.001 * (next(ticks) % 7)  # ... the agreed (max over ranks) value drives the session clock
+
+        out = router_sim.run_session(shard, pb, reqs, max_batch_size=6, text_of=lambda p: " ".join("x" for _ in p), agree=agree)
+        return out, len(calls)
+
+    a, n_a = session(1.0)
+    b, n_b = session(1000.0)
+    assert n_a == n_b == a["stats"]["prefill_calls"] + a["stats"]["decode_steps"]
+    assert a["tokens"] == b["tokens"]
+    for k in ("prefill_calls", "decode_steps", "decode_tokens", "batch_size_sum", "concat_steps", "max_batch", "sim_time_s"):
+        assert a["stats"][k] == b["stats"][k], k
