@@ -302,6 +302,16 @@ class FlashCausalLM(Model):
         reads back B ids (+ log-probabilities / ranks when asked) per step.  Plain greedy batches arg-max inside the C++ step
         (with the min_new_tokens EOS mask); sampling, penalties, top-k / top-p, logprobs and ranks go through the fused chooser
         kernel (csrc/chooser.cu).  Typical-p and top-n details stay on the op-by-op path."""
+        # the answer depends only on the requests and their chooser: asked every step, computed once per batch composition
+        # (prune installs a new requests list and chooser, concatenate a new batch)
+        memo = getattr(batch, "_can_fuse_memo", None)
+        if memo is not None and memo[0] is batch.requests and memo[1] is batch.next_token_chooser:
+            return memo[2]
+        answer = self._can_fuse_greedy_uncached(batch)
+        batch._can_fuse_memo = (batch.requests, batch.next_token_chooser, answer)
+        return answer
+
+    def _can_fuse_greedy_uncached(self, batch) -> bool:
         # families without the C++ step runtime (flash GPT-NeoX) run op by op unless their Python step is switched on
         if not getattr(self.model, "fused_greedy_enabled", hasattr(self.model, "make_step")):
             return False
